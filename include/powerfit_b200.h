@@ -1,0 +1,130 @@
+/*
+ * powerfit_b200 -- C ABI of the B200-native exhaustive LCC search.
+ *
+ * This is the drop-in boundary for the reference's `--gpu` correlator
+ * (/root/reference/src/powerfit_em/powerfitter.py:396-555, class GPUCorrelator, and the
+ * OpenCL/clFFT operators underneath it).  The reference has no FFI of its own for this
+ * path: its GPU backend is reached through pyopencl + gpyfft from Python.  The entry
+ * points below are what a maintainer binds with ctypes in place of those two packages
+ * (see INTEGRATION.md for the stub); each comment names the reference interface the
+ * function replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - Every function returns 0 on success and a non-zero code on failure;
+ *    pfb_last_error() returns a thread-local description of the last failure.
+ *  - Unless a parameter is documented as HOST, pointers are CUDA device pointers on the
+ *    plan's device.  `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *    stream).  Calls only enqueue work; the caller synchronises the stream.
+ *  - Grids are C-ordered (nz, ny, nx), x fastest, exactly like the reference's numpy
+ *    arrays.  Template and mask are centred on voxel (0,0,0) with periodic wrap-around.
+ *  - A plan is bound to one device and one grid shape.  It is not thread-safe; distinct
+ *    plans may be used concurrently.
+ *  - Supported axis lengths: any product of 2, 3, 5 and 7 (the set the reference's clFFT
+ *    backend supports and its CLI pads to, powerfit.py:230-233), each >= 2.
+ *    Other lengths fail with PFB_ERR_UNSUPPORTED (there is no CPU fallback).
+ */
+#ifndef POWERFIT_B200_H
+#define POWERFIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pfb_plan pfb_plan;
+
+enum {
+    PFB_OK = 0,
+    PFB_ERR_INVALID = 1,       /* bad argument / call order (ValueError in the reference)  */
+    PFB_ERR_UNSUPPORTED = 2,   /* axis length not 2.3.5.7-smooth, or shape too large        */
+    PFB_ERR_CUDA = 3,          /* a CUDA runtime call failed; see pfb_last_error()          */
+    PFB_ERR_NODEVICE = 4       /* no usable sm_100 device                                   */
+};
+
+/* Version / build info: "powerfit_b200 <ver> sm_100a". */
+const char *pfb_version(void);
+const char *pfb_last_error(void);
+
+/* GPUCorrelator.__init__/_allocate_arrays/_build_ffts (powerfitter.py:399-460):
+ * allocates every device buffer and FFT table for one (device, shape).
+ * max_batch = rotations in flight per pass (rounded up to even; 0 = choose).
+ * rmax is derived as min(nz,ny,nx)/2 (powerfitter.py:176). */
+int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan **out);
+int pfb_plan_destroy(pfb_plan *plan);
+
+/* Query: 0 nz, 1 ny, 2 nx, 3 rmax, 4 batch, 5 device, 6 fused-path-available,
+ * 7 kernel launches since plan creation (low 31 bits). */
+int pfb_plan_info(const pfb_plan *plan, int what, int64_t *value);
+
+/* GPUCorrelator.__init__ (powerfitter.py:410-420): takes the normalised (and, if the
+ * caller wants it, Laplace-filtered) target f and the lcc_mask (uint8, non-zero = score
+ * this voxel) and precomputes FFT(f) and FFT(f^2). */
+int pfb_set_target(pfb_plan *plan, const float *target, const uint8_t *lcc_mask, void *stream);
+
+/* GPUCorrelator.mask setter (powerfitter.py:466-474): uploads the prepared template
+ * (masked, z-scored, masked again -- powerfitter.py:204-220) and mask.  norm_factor is
+ * the number of non-zero mask voxels (powerfitter.py:199).  mask_is_binary != 0 promises
+ * mask in {0,1}, which lets the search skip the separate mask^2 transform. */
+int pfb_set_template(pfb_plan *plan, const float *tmpl, const float *mask, float norm_factor,
+                     int mask_is_binary, void *stream);
+
+/* Reset a packed best grid to "LCC 0, rotation 0" (glcc.fill(0), grot.fill(0),
+ * powerfitter.py:516-517). best = nz*ny*nx int64 packed keys: (orderable(lcc) << 32) | (0xFFFFFFFF - rot), signed order. */
+int pfb_best_init(pfb_plan *plan, int64_t *best, void *stream);
+
+/* GPUCorrelator.scan (powerfitter.py:513-538): for each of the R rotations
+ * (rotmats: HOST pointer, R*9 doubles, row-major 3x3 each, powerfitter.py:226-230)
+ * rotate template+mask, correlate with the target through FFTs, form the LCC and fold
+ * it into `best` with the reference's strict-greater / lowest-index-wins rule.
+ * Rotation n is recorded as index rot_index_offset + n (the offset is how a rank that
+ * owns a block of the rotation list reports global indices, powerfitter.py:159). */
+int pfb_scan(pfb_plan *plan, const double *rotmats_host, int R, int rot_index_offset,
+             int64_t *best, void *stream);
+
+/* Split the packed grid into the reference's outputs: lcc float32, rot int32
+ * (powerfitter.py:435-436, 536-537). */
+int pfb_unpack(pfb_plan *plan, const int64_t *best, float *lcc, int32_t *rot, void *stream);
+
+/* Element-wise max of two packed grids (dst = max(dst, src)); the on-device form of
+ * PowerFitter._combine (powerfitter.py:146-163) for partial results already on one GPU. */
+int pfb_merge_best(pfb_plan *plan, int64_t *dst, const int64_t *src, void *stream);
+
+/* Optional per-kernel timing for benchmarks: while enabled every launch is bracketed by
+ * CUDA events on its stream (adds a little overhead; never on during a timed run).
+ * pfb_profile(plan, 1) resets and starts, pfb_profile(plan, 0) stops.  pfb_profile_read
+ * returns accumulated milliseconds and launch count of kernel class `cls` (0 <= cls,
+ * PFB_ERR_INVALID past the last class) and its name.  (The reference has wall-clock
+ * timing only, powerfit.py:281-283.) */
+int pfb_profile(pfb_plan *plan, int enable);
+int pfb_profile_read(pfb_plan *plan, int cls, double *ms, int64_t *launches, const char **name);
+
+/* ---- operator-level entry points (unit parity with the reference operators) ---- */
+
+/* _extensions.rotate_grid3d (_extensions.c:7-196) / kernels.cl rotate_image3d
+ * (kernels.cl:162-226): out[r] (R grids of nz*ny*nx float32) = grid rotated by each
+ * matrix (HOST, R*9 doubles); voxels outside the rmax sphere are written as 0. */
+int pfb_rotate(pfb_plan *plan, const float *grid, const double *rotmats_host, int R, int nearest,
+               float *out, void *stream);
+
+/* grfftn_builder (powerfitter.py:605-638) / numpy.fft: in-place 3-D complex DFT with
+ * kernel exp(+2*pi*i*k*r/n), un-normalised, of `nvol` interleaved-complex64 volumes. */
+int pfb_fft3_c2c(pfb_plan *plan, float *vols_interleaved, int nvol, void *stream);
+
+/* CLKernels.calc_lcc_and_take_best (powerfitter.py:572-584): gcc/ave/ave2 float32 grids of
+ * one rotation; ave2 is multiplied by norm_factor inside, like the reference kernel. */
+int pfb_lcc_take_best(pfb_plan *plan, const float *gcc, const float *ave, const float *ave2,
+                      float norm_factor, int rot_index, int64_t *best, void *stream);
+
+/* Whole search with HOST buffers (what the Python GPUCorrelator does around scan():
+ * uploads, scan, downloads -- powerfitter.py:414-416, 471-474, 536-537).  All pointers
+ * HOST.  lcc/rot receive nz*ny*nx values. */
+int pfb_search_host(pfb_plan *plan, const float *target, const uint8_t *lcc_mask,
+                    const float *tmpl, const float *mask, float norm_factor, int mask_is_binary,
+                    const double *rotmats, int R, int rot_index_offset, float *lcc, int32_t *rot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POWERFIT_B200_H */

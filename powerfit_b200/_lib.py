@@ -1,0 +1,102 @@
+"""Loader (ctypes) and build recipe for the CUDA library ``libpowerfit_b200.so``.
+
+The library is built in-tree with nvcc for sm_100a only.  There is no CPU or PyTorch
+fallback: if the shared object is missing or cannot be loaded, every entry point of
+this package raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpowerfit_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+# every symbol include/powerfit_b200.h declares
+SYMBOLS = ["pfb_version", "pfb_last_error", "pfb_plan_create", "pfb_plan_destroy", "pfb_plan_info",
+           "pfb_set_target", "pfb_set_template", "pfb_best_init", "pfb_scan", "pfb_unpack",
+           "pfb_merge_best", "pfb_profile", "pfb_profile_read", "pfb_rotate", "pfb_fft3_c2c", "pfb_lcc_take_best", "pfb_search_host"]
+
+_lib = None
+
+
+class PowerfitB200Error(RuntimeError):
+    pass
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into libpowerfit_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(os.path.dirname(_HERE), "include", "powerfit_b200.h")]
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise PowerfitB200Error("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load the CUDA library, or raise (there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PowerfitB200Error(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "powerfit_b200 has no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, f32 = c.c_void_p, c.c_int, c.c_float
+    lib.pfb_version.restype = c.c_char_p
+    lib.pfb_last_error.restype = c.c_char_p
+    lib.pfb_plan_create.argtypes = [i32, i32, i32, i32, i32, c.POINTER(vp)]
+    lib.pfb_plan_destroy.argtypes = [vp]
+    lib.pfb_plan_info.argtypes = [vp, i32, c.POINTER(c.c_int64)]
+    lib.pfb_set_target.argtypes = [vp, vp, vp, vp]
+    lib.pfb_set_template.argtypes = [vp, vp, vp, f32, i32, vp]
+    lib.pfb_best_init.argtypes = [vp, vp, vp]
+    lib.pfb_scan.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.pfb_unpack.argtypes = [vp, vp, vp, vp, vp]
+    lib.pfb_merge_best.argtypes = [vp, vp, vp, vp]
+    lib.pfb_profile.argtypes = [vp, i32]
+    lib.pfb_profile_read.argtypes = [vp, i32, c.POINTER(c.c_double), c.POINTER(c.c_int64), c.POINTER(c.c_char_p)]
+    lib.pfb_rotate.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.pfb_fft3_c2c.argtypes = [vp, vp, i32, vp]
+    lib.pfb_lcc_take_best.argtypes = [vp, vp, vp, vp, f32, i32, vp, vp]
+    lib.pfb_search_host.argtypes = [vp, vp, vp, vp, vp, f32, i32, vp, i32, i32, vp, vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("pfb_version", "pfb_last_error"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Translate a status code: contract violations raise ValueError like the reference's
+    correlators do, everything else PowerfitB200Error."""
+    if rc == 0:
+        return
+    msg = load().pfb_last_error().decode("utf-8", "replace")
+    if rc == 1:
+        raise ValueError(msg)
+    raise PowerfitB200Error("powerfit_b200 error %d: %s" % (rc, msg))

@@ -1,0 +1,290 @@
+"""``CUDACorrelator`` -- the B200 drop-in for the reference's ``GPUCorrelator``.
+
+Same duck-typed contract as ``BaseCorrelator``/``GPUCorrelator``
+(/root/reference/src/powerfit_em/powerfitter.py:166-255, 396-555): constructor takes
+the target array (+ a device handle + ``laplace``), then ``.template``, ``.mask``,
+``.rotations`` are set in that order, ``.scan()`` runs the search and ``.lcc``
+(float32) / ``.rot`` (int32) hold the results.  The same ``ValueError`` messages are
+raised for the same contract violations.
+
+One-time host preparation (target normalisation, lcc_mask, Laplace filter, template
+z-scoring) follows the reference formulas in FP64 numpy and is then cast to FP32, like
+``GPUCorrelator`` does (powerfitter.py:414, 471-474).  Everything per-rotation runs in
+the hand-written sm_100a kernels behind the C ABI (``include/powerfit_b200.h``);
+PyTorch only provides device buffers, the stream and -- when a process group is
+initialised -- the single MAX all-reduce that merges the rotation shards.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from sys import stdout
+from time import time
+
+import numpy as np
+
+from . import _lib
+
+
+def _laplace_wrap(a):
+    """powerfitter.py:212-215 (scipy.ndimage.laplace, mode='wrap')."""
+    from scipy.ndimage import laplace
+    return laplace(a, mode="wrap")
+
+
+def shard_bounds(nrot, world, rank):
+    """Contiguous rotation blocks of nrot//world, last rank takes the remainder
+    (powerfitter.py:95-108)."""
+    per = nrot // world
+    lo = rank * per
+    hi = nrot if rank == world - 1 else lo + per
+    return lo, hi
+
+
+def _resolve_device(device):
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.PowerfitB200Error("CUDACorrelator needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        if "LOCAL_RANK" in os.environ:
+            return torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        return torch.device("cuda", torch.cuda.current_device())
+    if isinstance(device, int):
+        return torch.device("cuda", device)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("device must be a CUDA device")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class CUDACorrelator(object):
+    """B200 implementation of the local cross-correlation search."""
+
+    def __init__(self, target, device=None, laplace=False, batch=0):
+        import torch
+        self._torch = torch
+        self._libh = _lib.load()
+        target = np.asarray(target, dtype=np.float64)
+        if target.ndim != 3:
+            raise ValueError("target must be a 3-D array")
+        # BaseCorrelator.__init__, powerfitter.py:169-176
+        self._target = target / target.max()
+        self._rotations = None
+        self._template = None
+        self._mask = None
+        self._laplace = laplace
+        self._lcc_mask = (self._target > self._target.max() * 0.05).astype(np.uint8)
+        self._rmax = min(target.shape) // 2
+        self._lcc = None
+        self._rot = None
+        self.progress = False
+        self.shard = True           # split rotations over torch.distributed ranks when initialised
+        self.last_scan_seconds = None
+
+        self._device = _resolve_device(device)
+        self._plan = ctypes.c_void_p()
+        nz, ny, nx = target.shape
+        _lib.check(self._libh.pfb_plan_create(nz, ny, nx, int(batch), self._device.index,
+                                              ctypes.byref(self._plan)))
+        t = _laplace_wrap(self._target) if laplace else self._target      # powerfitter.py:410-412
+        with torch.cuda.device(self._device):
+            self._d_target = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(self._device)
+            self._d_lcc_mask = torch.from_numpy(np.ascontiguousarray(self._lcc_mask)).to(self._device)
+            self._best = torch.empty(target.size, dtype=torch.int64, device=self._device)
+            _lib.check(self._libh.pfb_set_target(self._plan, self._d_target.data_ptr(),
+                                                 self._d_lcc_mask.data_ptr(), self._stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self._libh.pfb_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self._device).cuda_stream)
+
+    def plan_info(self, what):
+        v = ctypes.c_int64()
+        _lib.check(self._libh.pfb_plan_info(self._plan, what, ctypes.byref(v)))
+        return v.value
+
+    @property
+    def kernel_launches(self):
+        return self.plan_info(7)
+
+    # ------------------------------------------------------------------ contract
+    @property
+    def target(self):
+        return self._target
+
+    @property
+    def template(self):
+        return self._template
+
+    @template.setter
+    def template(self, template):                      # powerfitter.py:236-243
+        template = np.asarray(template)
+        if template.shape != self._target.shape:
+            raise ValueError("Shape of template does not match the target.")
+        self._mask = None
+        self._template = np.array(template, dtype=np.float64)
+
+    @property
+    def mask(self):
+        return self._mask
+
+    @mask.setter
+    def mask(self, mask):                              # powerfitter.py:190-210, 466-474
+        if self._template is None:
+            raise ValueError("First set the template.")
+        mask = np.asarray(mask)
+        if self._target.shape != mask.shape:
+            raise ValueError("Shape of the mask is different from target.")
+        ind = mask != 0
+        self._norm_factor = ind.sum()
+        if self._norm_factor == 0:
+            raise ValueError("Zero-filled mask is not allowed.")
+        self._mask = np.array(mask, dtype=np.float64)
+        if self._laplace:
+            self._template = _laplace_wrap(self._template)
+        self._template *= self._mask
+        self._template[ind] -= self._template[ind].mean()       # powerfitter.py:217-220
+        self._template[ind] /= self._template[ind].std()
+        self._template *= self._mask
+        binary = bool(np.all(self._mask[ind] == 1.0))
+        torch = self._torch
+        with torch.cuda.device(self._device):
+            d_t = torch.from_numpy(np.ascontiguousarray(self._template, dtype=np.float32)).to(self._device)
+            d_m = torch.from_numpy(np.ascontiguousarray(self._mask, dtype=np.float32)).to(self._device)
+            _lib.check(self._libh.pfb_set_template(self._plan, d_t.data_ptr(), d_m.data_ptr(),
+                                                   float(self._norm_factor), int(binary), self._stream()))
+            torch.cuda.current_stream(self._device).synchronize()
+
+    @property
+    def rotations(self):
+        return self._rotations
+
+    @rotations.setter
+    def rotations(self, rotations):                    # powerfitter.py:226-230
+        self._rotations = np.ascontiguousarray(
+            np.asarray(rotations, dtype=np.float64).reshape(-1, 3, 3))
+
+    @property
+    def lcc(self):
+        return self._lcc
+
+    @property
+    def rot(self):
+        return self._rot
+
+    # ------------------------------------------------------------------ search
+    def scan_device(self, lo=None, hi=None, reset=True):
+        """Run rotations [lo, hi) (global indices) into the device-resident packed best
+        grid; no host transfer except the rotation matrices.  Returns the int64 tensor."""
+        if any(req is None for req in (self._template, self._mask, self._rotations)):
+            raise ValueError("First set the template, mask, and rotations.")
+        nrot = self._rotations.shape[0]
+        lo = 0 if lo is None else lo
+        hi = nrot if hi is None else hi
+        torch = self._torch
+        with torch.cuda.device(self._device):
+            s = self._stream()
+            if reset:
+                _lib.check(self._libh.pfb_best_init(self._plan, self._best.data_ptr(), s))
+            if self.progress:
+                step = max(2 * self.plan_info(4), (hi - lo) // 200)
+                time0 = time()
+                for a in range(lo, hi, step):
+                    b = min(hi, a + step)
+                    self._scan_block(a, b, s)
+                    torch.cuda.current_stream(self._device).synchronize()
+                    self._print_progress(b - lo - 1, hi - lo, time0)
+                stdout.write("\n")
+            else:
+                self._scan_block(lo, hi, s)
+        return self._best
+
+    def _scan_block(self, a, b, s):
+        sub = self._rotations[a:b]
+        _lib.check(self._libh.pfb_scan(self._plan, sub.ctypes.data_as(ctypes.c_void_p), b - a, a,
+                                       self._best.data_ptr(), s))
+
+    def scan(self):
+        """GPUCorrelator.scan (powerfitter.py:513-538).  With an initialised
+        torch.distributed process group (and ``self.shard``) each rank searches its
+        contiguous block of the rotation list and the packed best grids are merged by a
+        single integer MAX all-reduce; every rank ends with the full result."""
+        torch = self._torch
+        t0 = time()
+        nrot = 0 if self._rotations is None else self._rotations.shape[0]
+        world, rank = 1, 0
+        dist = torch.distributed
+        if self.shard and dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+        lo, hi = shard_bounds(nrot, world, rank)
+        best = self.scan_device(lo, hi)
+        if world > 1:
+            dist.all_reduce(best, op=dist.ReduceOp.MAX)
+        with torch.cuda.device(self._device):
+            lcc = torch.empty(self._target.shape, dtype=torch.float32, device=self._device)
+            rot = torch.empty(self._target.shape, dtype=torch.int32, device=self._device)
+            _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
+                                             self._stream()))
+            self._lcc = lcc.cpu().numpy()             # powerfitter.py:536-537
+            self._rot = rot.cpu().numpy()
+        self.last_scan_seconds = time() - t0
+
+    @staticmethod
+    def _print_progress(n, nrot, time0):               # powerfitter.py:540-547
+        p_done = (n + 1) / float(nrot) * 100
+        now = time()
+        eta = ((now - time0) / p_done) * (100 - p_done)
+        total = (now - time0) / p_done * (100)
+        stdout.write("{:7.2%} {:.0f}s {:.0f}s       \r".format(n / float(nrot), eta, total))
+        stdout.flush()
+
+    # ------------------------------------------------------------------ operator-level access
+    def rotate(self, grid, rotmats, nearest=False):
+        """Device twin of _extensions.rotate_grid3d for R rotations -> (R, nz, ny, nx) float32."""
+        torch = self._torch
+        rotmats = np.ascontiguousarray(np.asarray(rotmats, dtype=np.float64).reshape(-1, 3, 3))
+        R = rotmats.shape[0]
+        with torch.cuda.device(self._device):
+            g = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32)).to(self._device)
+            out = torch.empty((R,) + tuple(self._target.shape), dtype=torch.float32, device=self._device)
+            _lib.check(self._libh.pfb_rotate(self._plan, g.data_ptr(), rotmats.ctypes.data_as(ctypes.c_void_p),
+                                             R, int(bool(nearest)), out.data_ptr(), self._stream()))
+            return out.cpu().numpy()
+
+    def fft3(self, vols):
+        """In-place-style 3-D complex DFT, kernel exp(+2 pi i k r / n), un-normalised."""
+        torch = self._torch
+        v = np.ascontiguousarray(vols, dtype=np.complex64)
+        nvol = v.size // self._target.size
+        with torch.cuda.device(self._device):
+            d = torch.from_numpy(v.view(np.float32)).to(self._device)
+            _lib.check(self._libh.pfb_fft3_c2c(self._plan, d.data_ptr(), nvol, self._stream()))
+            return d.cpu().numpy().view(np.complex64).reshape(v.shape)
+
+    def lcc_take_best(self, gcc, ave, ave2, norm_factor, rot_index, best=None):
+        """Device twin of CLKernels.calc_lcc_and_take_best on host arrays; returns
+        (lcc, rot, best_tensor)."""
+        torch = self._torch
+        with torch.cuda.device(self._device):
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self._device)
+            g, a1, a2 = up(gcc), up(ave), up(ave2)
+            if best is None:
+                best = torch.empty(self._target.size, dtype=torch.int64, device=self._device)
+                _lib.check(self._libh.pfb_best_init(self._plan, best.data_ptr(), self._stream()))
+            _lib.check(self._libh.pfb_lcc_take_best(self._plan, g.data_ptr(), a1.data_ptr(), a2.data_ptr(),
+                                                    float(norm_factor), int(rot_index), best.data_ptr(),
+                                                    self._stream()))
+            lcc = torch.empty(self._target.shape, dtype=torch.float32, device=self._device)
+            rot = torch.empty(self._target.shape, dtype=torch.int32, device=self._device)
+            _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
+                                             self._stream()))
+            return lcc.cpu().numpy(), rot.cpu().numpy(), best

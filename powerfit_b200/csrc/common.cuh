@@ -1,0 +1,128 @@
+// Shared declarations of the powerfit_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/powerfit_b200.h"
+
+namespace pfb {
+
+void set_error(const std::string &msg);
+
+#define PFB_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            pfb::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));             \
+            return PFB_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define PFB_REQUIRE(cond, msg)                                                              \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            pfb::set_error(msg);                                                            \
+            return PFB_ERR_INVALID;                                                         \
+        }                                                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------- packed best key
+// key = (orderable(lcc) << 32) | (0xFFFFFFFF - rot) as a SIGNED 64-bit integer:
+// orderable() maps the float's bits to an int32 with the same order (-inf .. -0.0 <
+// +0.0 .. +inf), so a plain signed max means "greater LCC wins, equal LCC -> lower
+// rotation index wins" -- the reference's sequential strict-'>' rule
+// (powerfitter.py:327-330, 146-163) -- and the multi-GPU merge is one integer MAX
+// all-reduce.  pack(+0.0f, 0) is the initial value ("LCC 0, rotation 0").
+__host__ __device__ inline int32_t orderable_f32(uint32_t u) {
+    const int32_t s = (int32_t)u;
+    return s ^ ((s >> 31) & 0x7FFFFFFF);
+}
+__host__ __device__ inline uint32_t unorderable_f32(int32_t k) {
+    return (uint32_t)(k ^ ((k >> 31) & 0x7FFFFFFF));
+}
+__host__ __device__ inline int64_t pack_best(uint32_t lcc_bits, uint32_t rot) {
+    return (int64_t)(((uint64_t)(uint32_t)orderable_f32(lcc_bits) << 32) | (uint64_t)(0xFFFFFFFFu - rot));
+}
+constexpr int64_t kBestInit = 0x00000000FFFFFFFFll;  // (+0.0f, rot 0)
+
+// ---------------------------------------------------------------- 1-D FFT description
+constexpr int kMaxPasses = 16;
+struct Fft1D {
+    int n = 0;
+    int npass = 0;
+    int radix[kMaxPasses] = {0};
+};
+bool factorize(int n, Fft1D *out);   // radices from {8,4,2,3,5,7}; false if not smooth
+
+struct Plan;
+
+// kernel classes for the optional per-kernel timing (pfb_profile*)
+enum KernelClass { KC_ROTATE = 0, KC_FFT_X, KC_FFT_Y, KC_FFT_Z, KC_MULTIPLY, KC_LCC, KC_FUSED_A, KC_FUSED_B,
+                   KC_FUSED_C, KC_OTHER, KC_COUNT };
+const char *kernel_class_name(int cls);
+struct ProfRec { cudaEvent_t a, b; int cls; };
+
+// generic path (any 2.3.5.7-smooth shape)
+int launch_rotate_pack(Plan *p, const double *rot_dev, int first, int count, cudaStream_t s);
+int launch_fft_axis(Plan *p, float2 *vols, int nvol, int axis, cudaStream_t s);
+int fft_generic_init();
+int launch_multiply(Plan *p, int npairs, cudaStream_t s);
+int launch_lcc_best(Plan *p, int first_rot_index, int count, int64_t *best, cudaStream_t s);
+int launch_rotate_plain(Plan *p, const float *grid, const double *rot_dev, int R, int nearest,
+                        float *out, cudaStream_t s);
+int launch_lcc_single(Plan *p, const float *gcc, const float *ave, const float *ave2, float norm,
+                      int rot_index, int64_t *best, cudaStream_t s);
+int launch_best_init(Plan *p, int64_t *best, cudaStream_t s);
+int launch_unpack(Plan *p, const int64_t *best, float *lcc, int32_t *rot, cudaStream_t s);
+int launch_merge(Plan *p, int64_t *dst, const int64_t *src, cudaStream_t s);
+int launch_target_spectra(Plan *p, const float *target, cudaStream_t s);
+
+struct Plan {
+    int nz = 0, ny = 0, nx = 0, rmax = 0, device = 0;
+    long V = 0;
+    int batch = 0;            // rotations per pass (even)
+    int nsig = 2;             // forward volumes per rotation pair: 2 (binary mask) or 3
+    float norm_factor = 0.f;
+    bool have_target = false, have_template = false;
+    Fft1D fx, fy, fz;
+    float2 *tw[3] = {nullptr, nullptr, nullptr};   // exp(+2 pi i k/n) per axis (x,y,z)
+    float *tmpl = nullptr, *mask = nullptr;        // prepared template, mask (float32)
+    uint8_t *lcc_mask = nullptr;
+    float2 *F = nullptr, *F2 = nullptr;            // conj(P f)/V, conj(P f^2)/V, full spectra
+    float2 *A = nullptr;                           // forward work: [batch/2][3][V]
+    float2 *B = nullptr;                           // product / inverse work: [batch/2][3][V]
+    double *rot_dev = nullptr;
+    long rot_cap = 0;
+    int64_t *best_scratch = nullptr;              // used by pfb_search_host
+    unsigned long long launches = 0;
+    int sm_count = 148;
+    // per-kernel-class timing (off by default; events around every launch when on)
+    bool profile = false;
+    std::vector<ProfRec> prof;
+    double prof_ms[KC_COUNT] = {0};
+    long prof_n[KC_COUNT] = {0};
+};
+
+// RAII: counts the launch and, when profiling, brackets it with events on stream s.
+struct LaunchScope {
+    Plan *p; cudaStream_t s; cudaEvent_t b = nullptr;
+    LaunchScope(Plan *plan, int cls, cudaStream_t stream) : p(plan), s(stream) {
+        p->launches++;
+        if (p->profile) {
+            ProfRec r; r.cls = cls;
+            cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+            cudaEventRecord(r.a, s);
+            b = r.b;
+            p->prof.push_back(r);
+        }
+    }
+    ~LaunchScope() { if (b) cudaEventRecord(b, s); }
+};
+
+}  // namespace pfb
+
+struct pfb_plan {
+    pfb::Plan p;
+};

@@ -1,0 +1,121 @@
+"""CPU tests of the host-side logic: library loads and exports the C ABI, packing,
+rotation sharding, and the world_size-2 merge over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, golden_inputs
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from powerfit_b200 import _lib
+    path = _lib.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "powerfit_b200.h")).read()
+    declared = set(re.findall(r"\b(pfb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.pfb_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.pfb_version()
+
+
+def test_no_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from powerfit_b200 import CUDACorrelator, PowerfitB200Error
+    with pytest.raises(PowerfitB200Error):
+        CUDACorrelator(np.random.rand(8, 8, 8))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "powerfit_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", ""), f
+
+
+def test_packing_order_and_roundtrip():
+    from powerfit_b200 import packing as P
+    lcc = np.array([0.0, -0.0, 1e-30, -1e-30, 0.5, np.inf, -np.inf, 0.3, 0.3], dtype=np.float32)
+    rot = np.array([0, 3, 4, 5, 6, 7, 8, 5, 9])
+    key = P.pack(lcc, rot)
+    l2, r2 = P.unpack(key)
+    assert np.array_equal(l2.view(np.int32), lcc.view(np.int32)) and np.array_equal(r2, rot)
+    order = np.argsort(key)
+    assert list(lcc[order][:4]) == [-np.inf, np.float32(-1e-30), -0.0, 0.0]
+    assert P.pack(np.float32(0.3), 5) > P.pack(np.float32(0.3), 9)       # lower index wins ties
+    assert P.pack(np.float32(0.0), 0) == P.BEST_INIT
+    assert P.pack(np.float32(0.0), 7) < P.BEST_INIT                      # 0 never replaces the init
+    assert P.pack(np.float32(np.nan), 3) == P.BEST_INIT                  # NaN never wins
+    assert P.pack(np.float32(1e-38), 2 ** 31 - 2) > P.BEST_INIT
+
+
+def test_shard_bounds_match_reference_partition(oracle):
+    from powerfit_b200 import shard_bounds
+    for nrot, world in [(648, 8), (7416, 8), (10, 3), (5, 1), (7, 8)]:
+        want = oracle.partition_rotations(nrot, world)
+        got = [shard_bounds(nrot, world, r) for r in range(world)]
+        assert got == want
+
+
+def test_packed_merge_equals_reference_combine(oracle):
+    from powerfit_b200 import packing as P
+    g = load_golden("scan_24_laplace_cw")
+    target, template, mask = golden_inputs(g, "scan_24_laplace_cw")
+    R = g["rotations"]
+    blocks = oracle.partition_rotations(len(R), 3)
+    parts, keys = [], []
+    for a, b in blocks:
+        c = oracle.OracleCorrelator(target, laplace=True)
+        c.template, c.mask, c.rotations = template, mask, R[a:b]
+        c.scan()
+        parts.append((np.nan_to_num(c.lcc), c.rot))
+        keys.append(P.pack(c.lcc.astype(np.float32), c.rot + a))
+    lcc, rot = oracle.combine_partials(parts, len(R) // 3, target.shape)
+    ml, mr = P.unpack(np.maximum.reduce(keys))
+    assert np.allclose(ml, lcc, atol=1e-6)
+    assert np.array_equal(mr, rot.astype(np.int32))
+    assert np.allclose(ml, g["lcc"], atol=1e-6)
+
+
+WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from powerfit_b200 import packing as P, shard_bounds
+from oracle import oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+g = np.load(os.path.join(%(root)r, "tests", "golden", "scan_16x18x20_plain.npz"))
+target, template, mask = (g[k].astype(np.float64) for k in ("target", "template", "mask"))
+R = g["rotations"]
+lo, hi = shard_bounds(len(R), 2, dist.get_rank())
+c = O.OracleCorrelator(target); c.template = template; c.mask = mask; c.rotations = R[lo:hi]; c.scan()
+key = torch.from_numpy(P.pack(c.lcc.astype(np.float32), c.rot + lo))
+dist.all_reduce(key, op=dist.ReduceOp.MAX)
+lcc, rot = P.unpack(key.numpy())
+ok = np.allclose(lcc, g["lcc"], atol=1e-6)
+decided = (g["lcc"] - g["lcc2"]) > 1e-6
+ok = ok and np.array_equal(rot[decided], g["rot"][decided])
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_world_size_2_gloo_merge(tmp_path):
+    """The N>1 host path: shard -> per-rank partial -> packed int64 MAX all-reduce."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
+    codes = [p.wait(timeout=300) for p in procs]
+    assert codes == [0, 0]
