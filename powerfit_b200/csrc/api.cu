@@ -151,8 +151,15 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     PFB_ALLOC(p->A, sizeof(float2) * p->V * 3 * npairs);
     PFB_ALLOC(p->B, sizeof(float2) * p->V * 3 * npairs);
     PFB_ALLOC(p->best_scratch, sizeof(int64_t) * p->V);
+    p->fused = fused_supported(nz, ny, nx);
+    if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;
+    if (p->fused) {
+        PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
+        PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
+    }
 #undef PFB_ALLOC
     if ((rc = ensure_rot_capacity(p, 1024))) return fail(rc);
+    if (p->fused && (rc = fused_init(p))) return fail(rc);
     *out = h;
     return PFB_OK;
 }
@@ -162,7 +169,7 @@ int pfb_plan_destroy(pfb_plan *h) {
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch};
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     delete h;
@@ -179,7 +186,8 @@ int pfb_plan_info(const pfb_plan *h, int what, int64_t *value) {
         case 3: *value = p->rmax; break;
         case 4: *value = p->batch; break;
         case 5: *value = p->device; break;
-        case 6: *value = 0; break;
+        case 6: *value = p->fused ? 1 : 0; break;
+        case 8: *value = p->rs; break;
         case 7: *value = (int64_t)(p->launches & 0x7FFFFFFF); break;
         default: set_error("pfb_plan_info: unknown field"); return PFB_ERR_INVALID;
     }
@@ -221,6 +229,7 @@ int pfb_set_target(pfb_plan *h, const float *target, const uint8_t *lcc_mask, vo
     PFB_CUDA(cudaMemcpyAsync(p->lcc_mask, lcc_mask, p->V, cudaMemcpyDeviceToDevice, s));
     int rc = launch_target_spectra(p, target, s);
     if (rc) return rc;
+    if (p->fused && (rc = fused_prepare_target(p, s))) return rc;
     p->have_target = true;
     return PFB_OK;
 }
@@ -236,6 +245,10 @@ int pfb_set_template(pfb_plan *h, const float *tmpl, const float *mask, float no
     PFB_CUDA(cudaMemcpyAsync(p->mask, mask, sizeof(float) * p->V, cudaMemcpyDeviceToDevice, s));
     p->norm_factor = norm_factor;
     p->nsig = mask_is_binary ? 2 : 3;
+    if (p->fused) {
+        int rc = fused_prepare_template(p, s);
+        if (rc) return rc;
+    }
     p->have_template = true;
     return PFB_OK;
 }
@@ -261,7 +274,9 @@ int pfb_scan(pfb_plan *h, const double *rotmats_host, int R, int rot_index_offse
     PFB_CUDA(cudaMemcpyAsync(p->rot_dev, rotmats_host, sizeof(double) * 9 * R, cudaMemcpyHostToDevice, s));
     for (int first = 0; first < R; first += p->batch) {
         const int count = std::min(p->batch, R - first);
-        if ((rc = scan_batch_generic(p, first, count, rot_index_offset, best, s))) return rc;
+        rc = p->fused ? fused_batch(p, first, count, rot_index_offset, best, s)
+                      : scan_batch_generic(p, first, count, rot_index_offset, best, s);
+        if (rc) return rc;
     }
     return PFB_OK;
 }

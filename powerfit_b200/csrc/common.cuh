@@ -79,6 +79,13 @@ int launch_unpack(Plan *p, const int64_t *best, float *lcc, int32_t *rot, cudaSt
 int launch_merge(Plan *p, int64_t *dst, const int64_t *src, cudaStream_t s);
 int launch_target_spectra(Plan *p, const float *target, cudaStream_t s);
 
+// fused path (fused.cu)
+bool fused_supported(int nz, int ny, int nx);
+int fused_init(Plan *p);
+int fused_prepare_target(Plan *p, cudaStream_t s);
+int fused_prepare_template(Plan *p, cudaStream_t s);
+int fused_batch(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s);
+
 struct Plan {
     int nz = 0, ny = 0, nx = 0, rmax = 0, device = 0;
     long V = 0;
@@ -91,6 +98,11 @@ struct Plan {
     float *tmpl = nullptr, *mask = nullptr;        // prepared template, mask (float32)
     uint8_t *lcc_mask = nullptr;
     float2 *F = nullptr, *F2 = nullptr;            // conj(P f)/V, conj(P f^2)/V, full spectra
+    // fused path (cubic 64/128): map spectra transposed to [kx][ky][kz], template support box
+    bool fused = false;
+    float2 *Fq = nullptr, *F2q = nullptr;
+    int rs = 0, rs2 = 0;
+    unsigned ymask = 0;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]
     float2 *B = nullptr;                           // product / inverse work: [batch/2][3][V]
     double *rot_dev = nullptr;

@@ -287,3 +287,32 @@ def test_search_host_entry_point(pfb):
     _lib.check(lib.pfb_search_host(c._plan, p(t32), p(lm), p(tm32), p(m32), float(c._norm_factor), 1,
                                    p(R), len(R), 0, p(lcc), p(rot)))
     assert np.array_equal(lcc.reshape(target.shape), c.lcc) and np.array_equal(rot.reshape(target.shape), c.rot)
+
+
+@pytest.mark.parametrize("n,cw,laplace", [(64, False, False), (64, True, True), (128, True, False)])
+def test_fused_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace):
+    """The fused 3-kernel pipeline (cubic 64/128), with and without support pruning,
+    against the any-shape generic pipeline on the same inputs."""
+    from powerfit_b200 import synth
+    case = synth.make_case(n=n, voxelspacing=2.0 if n == 64 else 2.8, resolution=8.0, n_res=150, rg=12.0,
+                           n_copies=3, seed=21, core_weighted=cw)
+    rots = synth.random_rotations(7, seed=4)
+    results = {}
+    for mode, env in [("generic", {"PFB_FUSED": "0"}), ("fused", {"PFB_FUSED": "1"}),
+                      ("fused_noprune", {"PFB_FUSED": "1", "PFB_NO_PRUNE": "1"})]:
+        for k in ("PFB_FUSED", "PFB_NO_PRUNE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = run_scan(pfb, case.target, case.template, case.mask, rots, laplace, batch=4)
+        assert c.plan_info(6) == (0 if mode == "generic" else 1)
+        results[mode] = (c.lcc.copy(), c.rot.copy())
+    g_lcc, g_rot = results["generic"]
+    for mode in ("fused", "fused_noprune"):
+        lcc, rot = results[mode]
+        assert np.abs(lcc - g_lcc).max() < 2e-5, mode
+        same = rot == g_rot
+        assert same.mean() > 0.999, (mode, same.mean())
+        assert np.abs(lcc - g_lcc)[~same].max(initial=0) < 2e-5
+    assert np.array_equal(results["fused"][0], results["fused_noprune"][0])
+    assert np.array_equal(results["fused"][1], results["fused_noprune"][1])
