@@ -304,20 +304,33 @@ __device__ __forceinline__ void fold_best(int64_t &best, float gcc, float ave, f
     }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
+
+// One CTA owns a tile of 32 rows (fixed z, 32 consecutive y) and walks a chunk of rotation
+// pairs.  Per pair the three X2 tiles (ave2, ave, gcc) stream through a double-buffered
+// cp.async pipeline; thread (row r, t) transforms its row along x and keeps sqrt(var) of
+// its 16 voxels in registers until the gcc row arrives.  Tile layout [kx][34]: pitch 34
+// keeps 16-byte cp.async destinations aligned and, with the two pencils of a half-warp on
+// adjacent rows, every shared access conflict free.
 template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict__ lcc_mask, float norm,
                        int first_index, int count, int pairs_per_chunk, int64_t *__restrict__ best,
                        const float2 *__restrict__ twN) {
-    constexpr int E = N / 8, TP = 33, BP = N + 1;
+    constexpr int E = N / 8, TP = 34, BP = N + 1;
     extern __shared__ float2 smem[];
-    float2 *tile = smem;
-    int64_t *lbest = reinterpret_cast<int64_t *>(smem + N * TP);
+    float2 *tiles[2] = {smem, smem + N * TP};
+    int64_t *lbest = reinterpret_cast<int64_t *>(smem + 2 * N * TP);
     const int y0 = 32 * blockIdx.x, z = blockIdx.y;
     const int npairs = (count + 1) / 2;
     const int p0 = blockIdx.z * pairs_per_chunk, p1 = min(npairs, p0 + pairs_per_chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = lane & 7, r = warp + 8 * (lane >> 3);
+    const int t = lane & 7, r = 4 * warp + (lane >> 3);
     float2 tw[E];
     load_twiddles<E>(tw, twN, t);
     const size_t pl = (size_t)N * N;
@@ -328,42 +341,52 @@ fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict_
         if (lcc_mask[row + t + 8 * m]) mbits |= 1u << m;
         lbest[r * BP + t + 8 * m] = kBestInit;
     }
-    float2 a1[E], a2[E];
-    for (int p = p0; p < p1; ++p) {
+    const int nitems = 3 * (p1 - p0);
+    auto prefetch = [&](int item) {
+        const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
+        const float2 *src = X2 + ((size_t)(p * 3 + vol) * N) * pl + (size_t)z * N + y0;
+        float2 *dst = tiles[item & 1];
+        for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
+            const int kx = idx >> 4, ch = idx & 15;
+            cp_async16(dst + kx * TP + 2 * ch, src + (size_t)kx * pl + 2 * ch);
+        }
+        cp_async_commit();
+    };
+    if (nitems > 0) prefetch(0);
+    float2 sd[E];
+    for (int item = 0; item < nitems; ++item) {
+        if (item + 1 < nitems) { prefetch(item + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        float2 *tile = tiles[item & 1];
+        const int p = p0 + item / 3, vi = item % 3;
+        float2 v[E];
 #pragma unroll
-        for (int vi = 0; vi < 3; ++vi) {
-            const int vol = 2 - vi;                         // ave2, ave, gcc
-            const float2 *src = X2 + ((size_t)(p * 3 + vol) * N) * pl + (size_t)z * N + y0;
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
-                const int kx = idx >> 5, rr = idx & 31;
-                tile[kx * TP + rr] = __ldg(src + (size_t)kx * pl + rr);
+        for (int n1 = 0; n1 < E; ++n1) v[n1] = tile[(t + 8 * n1) * TP + r];
+        fft_pencil<E>(v, tile + r, TP, t, tw, true);
+        if (vi == 0) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) sd[m] = v[m];                  // ave2
+        } else if (vi == 1) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) {                              // sqrt(N ave2 - ave^2)
+                sd[m].x = __fsqrt_rn(__fsub_rn(__fmul_rn(sd[m].x, norm), __fmul_rn(v[m].x, v[m].x)));
+                sd[m].y = __fsqrt_rn(__fsub_rn(__fmul_rn(sd[m].y, norm), __fmul_rn(v[m].y, v[m].y)));
             }
-            __syncthreads();
-            float2 v[E];
+        } else {
+            const uint32_t ia = (uint32_t)(first_index + 2 * p);
+            const bool have_b = 2 * p + 1 < count;
 #pragma unroll
-            for (int n1 = 0; n1 < E; ++n1) v[n1] = tile[(t + 8 * n1) * TP + r];
-            fft_pencil<E>(v, tile + r, TP, t, tw, true);
-            if (vol == 2) {
-#pragma unroll
-                for (int m = 0; m < E; ++m) a2[m] = v[m];
-            } else if (vol == 1) {
-#pragma unroll
-                for (int m = 0; m < E; ++m) a1[m] = v[m];
-            } else {
-                const uint32_t ia = (uint32_t)(first_index + 2 * p);
-                const bool have_b = 2 * p + 1 < count;
-#pragma unroll
-                for (int m = 0; m < E; ++m) {
-                    if ((mbits >> m) & 1u) {
-                        int64_t b = lbest[r * BP + t + 8 * m];
-                        fold_best(b, v[m].x, a1[m].x, a2[m].x, norm, ia);
-                        if (have_b) fold_best(b, v[m].y, a1[m].y, a2[m].y, norm, ia + 1);
-                        lbest[r * BP + t + 8 * m] = b;
-                    }
+            for (int m = 0; m < E; ++m) {
+                if ((mbits >> m) & 1u) {
+                    int64_t b = lbest[r * BP + t + 8 * m];
+                    const float la = __fdiv_rn(v[m].x, sd[m].x), lb = __fdiv_rn(v[m].y, sd[m].y);
+                    if (la == la) { const int64_t k = pack_best(__float_as_uint(la), ia); if (k > b) b = k; }
+                    if (have_b && lb == lb) { const int64_t k = pack_best(__float_as_uint(lb), ia + 1); if (k > b) b = k; }
+                    lbest[r * BP + t + 8 * m] = b;
                 }
             }
         }
+        __syncthreads();       // everyone is done with this buffer before it is refilled
     }
 #pragma unroll
     for (int m = 0; m < E; ++m) {
@@ -411,7 +434,7 @@ template <int N> static int fused_init_n() {
     PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256)>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(N * (N + 1) * sizeof(float2))));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(N * TP * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t))));
+                                  (int)(2 * N * 34 * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t))));
     return PFB_OK;
 }
 
@@ -485,7 +508,7 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
         fused_ifftx_lcc_kernel<N><<<dim3(N / 32, N, chunks), 256,
-                                    N * TP * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t), s>>>(
+                                    2 * N * 34 * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t), s>>>(
             p->B, p->lcc_mask, p->norm_factor, rot_index_offset + first, count, ppc, best, p->tw[0]);
     }
     PFB_CUDA(cudaGetLastError());

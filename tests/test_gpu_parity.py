@@ -118,8 +118,9 @@ def test_lcc_take_best_edge_cases(pfb, oracle):
         ave2 = (rng.random(n).astype(np.float32) + 0.5)
         ave2[10] = ave[10] ** 2 / norm * 0.5        # negative variance -> NaN
         ave2[11] = 0.0; ave[11] = 0.0; gcc[11] = abs(gcc[11]) + 0.1     # zero variance -> +inf
+        gcc[12], ave[12], ave2[12] = -1.0, 0.5, 1.0
         if r in (2, 4):
-            gcc[12], ave[12], ave2[12] = 0.75, 0.5, 1.0                # exact tie between r=2 and r=4
+            gcc[12] = 0.75                                             # exact tie between r=2 and r=4
         lcc, rot, best = c.lcc_take_best(gcc.reshape(shape), ave.reshape(shape), ave2.reshape(shape),
                                          norm, r, best)
         scan = np.zeros(n)
@@ -258,11 +259,11 @@ def test_full_size_properties_128(pfb):
     rng = np.random.default_rng(0)
     # map = template shifted by a known vector (+ nothing else): perfect fit
     shift = (17, 90, 41)
-    target = np.roll(case.template, shift, axis=(0, 1, 2)) + 0.1 * case.template.max()
+    target = np.roll(case.template, shift, axis=(0, 1, 2)) + case.template.max() * (0.1 + 0.01 * rng.random((n, n, n)))
     rots = synth.random_rotations(4, seed=1)            # rots[0] is the identity
     c = run_scan(pfb, target, case.template, case.mask, rots, False)
     peak = np.unravel_index(np.argmax(c.lcc), c.lcc.shape)
-    assert peak == shift and abs(c.lcc[peak] - 1) < 1e-3 and c.rot[peak] == 0
+    assert peak == shift and abs(c.lcc[peak] - 1) < 2e-2 and c.rot[peak] == 0
     c2 = run_scan(pfb, 7.5 * target, case.template, case.mask, rots, False)
     assert np.abs(c2.lcc - c.lcc).max() < 1e-4 and np.array_equal(c2.rot, c.rot)
 
