@@ -2,10 +2,10 @@
 //
 //   A  fused_rotate_fftx  : rotate template+mask (a PAIR of rotations packed as one complex
 //                           signal: re = rotation a, im = rotation b), transform along x,
-//                           write X1[pair][sig][kx][z][y]            (replaces K1/K2 + 1/3 of K5)
+//                           write X1[pair][sig][z][kx][y]            (replaces K1/K2 + 1/3 of K5)
 //   B  fused_fftyz_mul    : one (kx, output volume, pair) plane per CTA, 128 KB of shared
 //                           memory: forward y, forward z, multiply with FT(map) or FT(map^2),
-//                           inverse z, inverse y, write X2[pair][vol][kx][z][y]
+//                           inverse z, inverse y, write X2[pair][vol][z][kx][y]
 //                                                                    (2/3 of K5, K6, 2/3 of K7)
 //   C  fused_ifftx_lcc    : inverse x of the gcc/ave/ave2 rows, LCC normalisation and the
 //                           running arg-max in registers/shared memory (1/3 of K7, K8-K10)
@@ -153,13 +153,21 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
     const int oz = z <= N / 2 ? z : z - N;
 
     // ---- gather the 32 x N tile of both signals (zeros outside the sphere / support)
-    for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
-        const int r = idx / N, x = idx % N;
+    //      zero-fill first, then visit only the x offsets inside the support box [xlo, rs];
+    //      offset -N/2 is skipped: it aliases index N/2, which belongs to offset +N/2.
+    for (int idx = threadIdx.x; idx < N * TP; idx += 256) {
+        tile_t[idx] = make_float2(0.f, 0.f);
+        tile_m[idx] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int xlo = max(-rs, -(N / 2 - 1)), W = rs - xlo + 1;
+    const int lim2 = min(rs2, (N / 2) * (N / 2));
+    for (int idx = threadIdx.x; idx < 32 * W; idx += 256) {
+        const int r = idx / W, ox = idx % W + xlo;
         const int iy = y0 + r;
-        const int oy = iy <= N / 2 ? iy : iy - N, ox = x <= N / 2 ? x : x - N;
-        const int d2 = ox * ox + oy * oy + oz * oz;
-        float2 tv = make_float2(0.f, 0.f), mv = make_float2(0.f, 0.f);
-        if (d2 <= (N / 2) * (N / 2) && d2 <= rs2) {
+        const int oy = iy <= N / 2 ? iy : iy - N;
+        if (ox * ox + oy * oy + oz * oz <= lim2) {
+            float2 tv = make_float2(0.f, 0.f), mv = make_float2(0.f, 0.f);
             const SrcCoord ca = source_coord(Ra, ox, oy, oz);
             tv.x = sample_trilinear(tmpl, d, ca);
             mv.x = sample_nearest(mask, d, ca);
@@ -168,9 +176,10 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
                 tv.y = sample_trilinear(tmpl, d, cb);
                 mv.y = sample_nearest(mask, d, cb);
             }
+            const int x = ox < 0 ? ox + N : ox;
+            tile_t[x * TP + r] = tv;
+            tile_m[x * TP + r] = mv;
         }
-        tile_t[x * TP + r] = tv;
-        tile_m[x * TP + r] = mv;
     }
     __syncthreads();
 
@@ -197,12 +206,12 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
 
     // ---- coalesced write-out: 32 consecutive y (256 B) per kx
     const size_t plane = (size_t)N * N;
-    float2 *o_t = X1 + ((size_t)(pair * nsig + 0) * N) * plane + (size_t)z * N + y0;
-    float2 *o_m = X1 + ((size_t)(pair * nsig + 1) * N) * plane + (size_t)z * N + y0;
+    float2 *o_t = X1 + ((size_t)(pair * nsig + 0) * N + z) * plane + y0;      // X1[pair][sig][z][kx][y]
+    float2 *o_m = X1 + ((size_t)(pair * nsig + 1) * N + z) * plane + y0;
     for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
         const int kx = idx >> 5, rr = idx & 31;
-        o_t[(size_t)kx * plane + rr] = tile_t[kx * TP + rr];
-        o_m[(size_t)kx * plane + rr] = tile_m[kx * TP + rr];
+        o_t[(size_t)kx * N + rr] = tile_t[kx * TP + rr];
+        o_m[(size_t)kx * N + rr] = tile_m[kx * TP + rr];
     }
     if (nsig == 3) {
         __syncthreads();
@@ -210,10 +219,10 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
 #pragma unroll
         for (int m = 0; m < E; ++m) tile_t[(t + 8 * m) * TP + r] = v2[m];
         __syncthreads();
-        float2 *o_2 = X1 + ((size_t)(pair * nsig + 2) * N) * plane + (size_t)z * N + y0;
+        float2 *o_2 = X1 + ((size_t)(pair * nsig + 2) * N + z) * plane + y0;
         for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
             const int kx = idx >> 5, rr = idx & 31;
-            o_2[(size_t)kx * plane + rr] = tile_t[kx * TP + rr];
+            o_2[(size_t)kx * N + rr] = tile_t[kx * TP + rr];
         }
     }
 }
@@ -229,9 +238,9 @@ fused_fftyz_mul_kernel(const float2 *__restrict__ X1, float2 *__restrict__ X2, c
     const int kx = blockIdx.x, vol = blockIdx.y, pair = blockIdx.z;
     const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
     const size_t pl = (size_t)N * N;
-    const float2 *src = X1 + ((size_t)(pair * nsig + sig) * N + kx) * pl;
+    const float2 *src = X1 + (size_t)(pair * nsig + sig) * N * pl + (size_t)kx * N;   // + z*pl + y
     const float2 *Fm = (vol == 2 ? F2q : Fq) + (size_t)kx * pl;
-    float2 *dst = X2 + ((size_t)(pair * 3 + vol) * N + kx) * pl;
+    float2 *dst = X2 + (size_t)(pair * 3 + vol) * N * pl + (size_t)kx * N;            // + z*pl + y
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = THREADS / 32;
     const int t = lane & 7, c = lane >> 3;
@@ -249,7 +258,7 @@ fused_fftyz_mul_kernel(const float2 *__restrict__ X1, float2 *__restrict__ X2, c
 #pragma unroll
         for (int n1 = 0; n1 < E; ++n1) {
             const int y = t + 8 * n1;
-            v[n1] = (act && ((ymask >> (y >> 5)) & 1u)) ? __ldg(src + (size_t)z * N + y) : make_float2(0.f, 0.f);
+            v[n1] = (act && ((ymask >> (y >> 5)) & 1u)) ? __ldg(src + (size_t)z * pl + y) : make_float2(0.f, 0.f);
         }
         fft_pencil<E>(v, plane + z * P, 1, t, tw, act);
         if (act) {
@@ -289,7 +298,7 @@ fused_fftyz_mul_kernel(const float2 *__restrict__ X1, float2 *__restrict__ X2, c
         for (int n1 = 0; n1 < E; ++n1) v[n1] = plane[z * P + t + 8 * n1];
         fft_pencil<E>(v, plane + z * P, 1, t, tw, true);
 #pragma unroll
-        for (int m = 0; m < E; ++m) dst[(size_t)z * N + t + 8 * m] = v[m];
+        for (int m = 0; m < E; ++m) dst[(size_t)z * pl + t + 8 * m] = v[m];
     }
 }
 
@@ -344,11 +353,11 @@ fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict_
     const int nitems = 3 * (p1 - p0);
     auto prefetch = [&](int item) {
         const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
-        const float2 *src = X2 + ((size_t)(p * 3 + vol) * N) * pl + (size_t)z * N + y0;
+        const float2 *src = X2 + ((size_t)(p * 3 + vol) * N + z) * pl + y0;
         float2 *dst = tiles[item & 1];
         for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
             const int kx = idx >> 4, ch = idx & 15;
-            cp_async16(dst + kx * TP + 2 * ch, src + (size_t)kx * pl + 2 * ch);
+            cp_async16(dst + kx * TP + 2 * ch, src + (size_t)kx * N + 2 * ch);
         }
         cp_async_commit();
     };
@@ -368,9 +377,10 @@ fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict_
             for (int m = 0; m < E; ++m) sd[m] = v[m];                  // ave2
         } else if (vi == 1) {
 #pragma unroll
-            for (int m = 0; m < E; ++m) {                              // sqrt(N ave2 - ave^2)
-                sd[m].x = __fsqrt_rn(__fsub_rn(__fmul_rn(sd[m].x, norm), __fmul_rn(v[m].x, v[m].x)));
-                sd[m].y = __fsqrt_rn(__fsub_rn(__fmul_rn(sd[m].y, norm), __fmul_rn(v[m].y, v[m].y)));
+            for (int m = 0; m < E; ++m) {                              // 1/sqrt(N ave2 - ave^2)
+                // var <= 0 gives inf / NaN exactly where the reference's gcc/sqrt(var) does
+                sd[m].x = rsqrtf(__fsub_rn(__fmul_rn(sd[m].x, norm), __fmul_rn(v[m].x, v[m].x)));
+                sd[m].y = rsqrtf(__fsub_rn(__fmul_rn(sd[m].y, norm), __fmul_rn(v[m].y, v[m].y)));
             }
         } else {
             const uint32_t ia = (uint32_t)(first_index + 2 * p);
@@ -379,7 +389,7 @@ fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict_
             for (int m = 0; m < E; ++m) {
                 if ((mbits >> m) & 1u) {
                     int64_t b = lbest[r * BP + t + 8 * m];
-                    const float la = __fdiv_rn(v[m].x, sd[m].x), lb = __fdiv_rn(v[m].y, sd[m].y);
+                    const float la = __fmul_rn(v[m].x, sd[m].x), lb = __fmul_rn(v[m].y, sd[m].y);
                     if (la == la) { const int64_t k = pack_best(__float_as_uint(la), ia); if (k > b) b = k; }
                     if (have_b && lb == lb) { const int64_t k = pack_best(__float_as_uint(lb), ia + 1); if (k > b) b = k; }
                     lbest[r * BP + t + 8 * m] = b;
