@@ -169,7 +169,7 @@ int pfb_plan_destroy(pfb_plan *h) {
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q};
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     delete h;

@@ -101,6 +101,7 @@ struct Plan {
     // fused path (cubic 64/128): map spectra transposed to [kx][ky][kz], template support box
     bool fused = false;
     float2 *Fq = nullptr, *F2q = nullptr;
+    float2 *twdN = nullptr, *twdM = nullptr;       // packed-pencil twiddle tables [k1][t] (fft_core.cuh)
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]

@@ -24,6 +24,7 @@
 // thread u finishes with the 8-point DFTs of k1 = u, u+8, ...; its outputs are X[u + 8m],
 // i.e. the same distribution the inputs had, in natural order -- no digit reversal.
 #include "common.cuh"
+#include "fft_core.cuh"
 #include "rotate_device.cuh"
 
 #include <algorithm>
@@ -31,102 +32,6 @@
 #include <cstdlib>
 
 namespace pfb {
-
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmulf(float2 a, float2 w) {
-    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
-}
-__device__ __forceinline__ float2 mul_i(float2 a) { return make_float2(-a.y, a.x); }
-
-// 4-point DFT, kernel exp(+2 pi i nk/4); results X0..X3 land in a, b, c, d
-__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
-    const float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = mul_i(csub(b, d));
-    a = cadd(s0, s1);
-    c = csub(s0, s1);
-    b = cadd(d0, d1);
-    d = csub(d0, d1);
-}
-
-__device__ __forceinline__ void dft8(float2 (&v)[8]) {
-    dft4(v[0], v[2], v[4], v[6]);
-    dft4(v[1], v[3], v[5], v[7]);
-    const float h = 0.70710678118654752440f;
-    const float2 t0 = v[1];
-    const float2 t1 = make_float2(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y));
-    const float2 t2 = mul_i(v[5]);
-    const float2 t3 = make_float2(h * (-v[7].x - v[7].y), h * (v[7].x - v[7].y));
-    const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
-    v[0] = cadd(e0, t0); v[4] = csub(e0, t0);
-    v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
-    v[2] = cadd(e2, t2); v[6] = csub(e2, t2);
-    v[3] = cadd(e3, t3); v[7] = csub(e3, t3);
-}
-
-__device__ __forceinline__ void dft16(float2 (&v)[16]) {
-#pragma unroll
-    for (int lo = 0; lo < 4; ++lo) dft4(v[lo], v[lo + 4], v[lo + 8], v[lo + 12]);
-    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
-    // v[lo + 4 k1] *= W16^(lo k1)
-    v[5] = cmulf(v[5], make_float2(c1, s1));                                  // 1*1
-    v[9] = make_float2(h * (v[9].x - v[9].y), h * (v[9].x + v[9].y));         // 1*2 -> W16^2
-    v[13] = cmulf(v[13], make_float2(s1, c1));                                // 1*3
-    v[6] = make_float2(h * (v[6].x - v[6].y), h * (v[6].x + v[6].y));         // 2*1
-    v[10] = mul_i(v[10]);                                                     // 2*2 -> W16^4
-    v[14] = make_float2(h * (-v[14].x - v[14].y), h * (v[14].x - v[14].y));   // 2*3 -> W16^6
-    v[7] = cmulf(v[7], make_float2(s1, c1));                                  // 3*1
-    v[11] = make_float2(h * (-v[11].x - v[11].y), h * (v[11].x - v[11].y));   // 3*2 -> W16^6
-    v[15] = cmulf(v[15], make_float2(-c1, -s1));                              // 3*3 -> W16^9
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
-    // X[k1 + 4 k2] sits in v[4 k1 + k2]: transpose the 4x4 register tile
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = a + 1; b < 4; ++b) { const float2 tmp = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = tmp; }
-}
-
-template <int E> __device__ __forceinline__ void dft_reg(float2 (&v)[E]);
-template <> __device__ __forceinline__ void dft_reg<8>(float2 (&v)[8]) { dft8(v); }
-template <> __device__ __forceinline__ void dft_reg<16>(float2 (&v)[16]) { dft16(v); }
-
-// N = 8E point transform of one pencil by the 8 threads t = 0..7 of a warp octet.
-// in : v[n1] = x[t + 8 n1]       out: v[m] = X[t + 8 m]
-// scratch[p * stride], p < N, is the pencil's shared-memory storage (clobbered).
-template <int E>
-__device__ __forceinline__ void fft_pencil(float2 (&v)[E], float2 *scratch, int stride, int t,
-                                           const float2 (&tw)[E], bool active) {
-    dft_reg<E>(v);
-#pragma unroll
-    for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulf(v[k1], tw[k1]);
-    __syncwarp();
-    if (active) {
-#pragma unroll
-        for (int k1 = 0; k1 < E; ++k1) scratch[(k1 * 8 + (t ^ (k1 & 7))) * stride] = v[k1];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < E / 8; ++q) {
-        float2 a[8];
-        if (active) {
-#pragma unroll
-            for (int n0 = 0; n0 < 8; ++n0) a[n0] = scratch[((t + 8 * q) * 8 + (n0 ^ t)) * stride];
-        } else {
-#pragma unroll
-            for (int n0 = 0; n0 < 8; ++n0) a[n0] = make_float2(0.f, 0.f);
-        }
-        dft8(a);
-#pragma unroll
-        for (int k0 = 0; k0 < 8; ++k0) v[(E / 8) * k0 + q] = a[k0];
-    }
-    __syncwarp();
-}
-
-template <int E>
-__device__ __forceinline__ void load_twiddles(float2 (&tw)[E], const float2 *__restrict__ twN, int t) {
-#pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) tw[k1] = __ldg(twN + t * k1);      // t*k1 < 8E = N
-}
 
 // ------------------------------------------------------------------------------- kernel A
 template <int N>
@@ -204,14 +109,19 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
     for (int m = 0; m < E; ++m) tile_m[(t + 8 * m) * TP + r] = v[m];
     __syncthreads();
 
-    // ---- coalesced write-out: 32 consecutive y (256 B) per kx
-    const size_t plane = (size_t)N * N;
-    float2 *o_t = X1 + ((size_t)(pair * nsig + 0) * N + z) * plane + y0;      // X1[pair][sig][z][kx][y]
-    float2 *o_m = X1 + ((size_t)(pair * nsig + 1) * N + z) * plane + y0;
-    for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
-        const int kx = idx >> 5, rr = idx & 31;
-        o_t[(size_t)kx * N + rr] = tile_t[kx * TP + rr];
-        o_m[(size_t)kx * N + rr] = tile_m[kx * TP + rr];
+    // ---- coalesced write-out: 32 consecutive y (256 B) per kx, pairs of y interleaved
+    //      (re[y], re[y+1], im[y], im[y+1]) -- the layout kernel B's packed passes work in
+    constexpr int H = N / 2;
+    const size_t slab = (size_t)N * H;
+    float4 *X14 = reinterpret_cast<float4 *>(X1);
+    float4 *o_t = X14 + ((size_t)(pair * nsig + 0) * N + z) * slab + y0 / 2;      // X1[pair][sig][z][kx][y/2]
+    float4 *o_m = X14 + ((size_t)(pair * nsig + 1) * N + z) * slab + y0 / 2;
+    for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
+        const int kx = idx >> 4, jj = idx & 15;
+        const float2 a = tile_t[kx * TP + 2 * jj], b = tile_t[kx * TP + 2 * jj + 1];
+        o_t[(size_t)kx * H + jj] = make_float4(a.x, b.x, a.y, b.y);
+        const float2 c = tile_m[kx * TP + 2 * jj], e = tile_m[kx * TP + 2 * jj + 1];
+        o_m[(size_t)kx * H + jj] = make_float4(c.x, e.x, c.y, e.y);
     }
     if (nsig == 3) {
         __syncthreads();
@@ -219,87 +129,166 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
 #pragma unroll
         for (int m = 0; m < E; ++m) tile_t[(t + 8 * m) * TP + r] = v2[m];
         __syncthreads();
-        float2 *o_2 = X1 + ((size_t)(pair * nsig + 2) * N + z) * plane + y0;
-        for (int idx = threadIdx.x; idx < 32 * N; idx += 256) {
-            const int kx = idx >> 5, rr = idx & 31;
-            o_2[(size_t)kx * N + rr] = tile_t[kx * TP + rr];
+        float4 *o_2 = X14 + ((size_t)(pair * nsig + 2) * N + z) * slab + y0 / 2;
+        for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
+            const int kx = idx >> 4, jj = idx & 15;
+            const float2 a = tile_t[kx * TP + 2 * jj], b = tile_t[kx * TP + 2 * jj + 1];
+            o_2[(size_t)kx * H + jj] = make_float4(a.x, b.x, a.y, b.y);
         }
     }
 }
 
 // ------------------------------------------------------------------------------- kernel B
-template <int N, int THREADS>
+// Work-buffer layout (X1 and X2 alike): [pair][volume][z][kx][y/2] of float4 =
+// (re[y], re[y+1], im[y], im[y+1]) -- two neighbouring y of one complex grid per 16 bytes, so
+// that every pass below works on packed pairs (fft_core.cuh) without any re-shuffling:
+//   phase 1  rows (fixed z), forward y : adjacent-in -> split-out, plane[z][ky] = (Y[ky], Y[ky+N/2])
+//   phase 2  columns ky and ky+N/2 as two independent pencils: forward z, multiply with the
+//            map spectrum (stored in the same pairing, Fpk[kx][ky][kz]), inverse z
+//   phase 3  rows, inverse y : split-in -> adjacent-out, straight to X2
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
+
+template <int N> struct FusedCfg;
+template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8; };
+template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8; };
+
+// Persistent: one CTA per SM walks the (kx, volume, pair) planes q = blockIdx.x, + gridDim.x, ...
+// While a plane is in phase 2, cp.async pulls the support rows of the CTA's NEXT plane into a
+// staging buffer; the row loop then does phase 3 of the current plane and phase 1 of the next
+// one row by row (a row's storage is free for the next plane the moment its inverse transform
+// has left for HBM), so there are two block barriers per plane, phase 1 never waits on HBM and
+// nothing drains between planes.  `staged` = 0 (support box too large for the staging buffer)
+// falls back to direct loads in phase 1.
+template <int N, int THREADS, bool STAGED>
 __global__ void __launch_bounds__(THREADS, 1)
-fused_fftyz_mul_kernel(const float2 *__restrict__ X1, float2 *__restrict__ X2, const float2 *__restrict__ Fq,
-                       const float2 *__restrict__ F2q, const float2 *__restrict__ twN, int rs, unsigned ymask,
-                       int nsig) {
-    constexpr int E = N / 8, P = N + 1;
-    extern __shared__ float2 plane[];
-    const int kx = blockIdx.x, vol = blockIdx.y, pair = blockIdx.z;
-    const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
-    const size_t pl = (size_t)N * N;
-    const float2 *src = X1 + (size_t)(pair * nsig + sig) * N * pl + (size_t)kx * N;   // + z*pl + y
-    const float2 *Fm = (vol == 2 ? F2q : Fq) + (size_t)kx * pl;
-    float2 *dst = X2 + (size_t)(pair * 3 + vol) * N * pl + (size_t)kx * N;            // + z*pl + y
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fpk,
+                       const float4 *__restrict__ F2pk, const float2 *__restrict__ twN_g,
+                       const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g, int rs,
+                       unsigned ymask, int nsig, int nplanes) {
+    using Cfg = FusedCfg<N>;
+    constexpr int H = N / 2, P = H + 1;
+    constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
+    constexpr int LM = Cfg::LM, EM = Cfg::EM, GM = 32 / LM;      // row pencils: packed N/2 points
     constexpr int NW = THREADS / 32;
-    const int t = lane & 7, c = lane >> 3;
-    float2 tw[E];
-    load_twiddles<E>(tw, twN, t);
-
-    // ---- phase 1: forward y of the rows inside the support box, global -> shared
+    extern __shared__ float4 smem4[];
+    float4 *plane = smem4;                                        // [N][P]
+    float4 *dummy = plane + N * P;                                // [GM][P] scratch rows of idle lanes
+    float2 *twN = reinterpret_cast<float2 *>(dummy + GM * P);     // [EN][LN] W_N^(t k1)
+    float2 *twM = twN + N;                                        // [EM][LM] W_H^(t k1)
+    float2 *twh_s = twM + H;                                      // [H] W_N^k of the split radix-2 step
+    float4 *stage = reinterpret_cast<float4 *>(twh_s + H);        // [nzv][nyp] support rows of the next plane
+    const size_t slab = (size_t)N * H;                                                 // float4 per z
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tM = lane & (LM - 1), gM = lane / LM;
+    const int tN = lane & (LN - 1), gN = lane / LN;
     const int nzv = min(2 * rs + 1, N);
-    const int ntask1 = ((nzv + 31) / 32) * 8;
-    for (int w = warp; w < ntask1; w += NW) {
-        const int j = 32 * (w >> 3) + (w & 7) + 8 * c;
-        const bool act = j < nzv;
-        const int z = act ? (j - rs + N) % N : 0;
-        float2 v[E];
-#pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) {
-            const int y = t + 8 * n1;
-            v[n1] = (act && ((ymask >> (y >> 5)) & 1u)) ? __ldg(src + (size_t)z * pl + y) : make_float2(0.f, 0.f);
-        }
-        fft_pencil<E>(v, plane + z * P, 1, t, tw, act);
-        if (act) {
-#pragma unroll
-            for (int m = 0; m < E; ++m) plane[z * P + t + 8 * m] = v[m];
-        }
-    }
-    __syncthreads();
+    const int nyp = 16 * __popc(ymask);                                                // y pairs per staged row
 
-    // ---- phase 2: forward z, multiply with the map spectrum, inverse z (columns ky)
-    for (int w = warp; w < N / 4; w += NW) {
-        const int ky = 32 * (w >> 3) + (w & 7) + 8 * c;
-        float2 f[E];
-#pragma unroll
-        for (int m = 0; m < E; ++m) f[m] = __ldg(Fm + (size_t)ky * N + t + 8 * m);
-        float2 v[E];
-#pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) {
-            const int z = t + 8 * n1;
-            const int sz = z <= N / 2 ? z : z - N;
-            v[n1] = (sz >= -rs && sz <= rs) ? plane[z * P + ky] : make_float2(0.f, 0.f);
+    auto plane_src = [&](int q) {
+        const int kx = q % N, vol = (q / N) % 3, pair = q / (3 * N);
+        const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+        return X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;           // + z*slab + y/2
+    };
+    auto prefetch_rows = [&](int q) {
+        if (STAGED && q < nplanes) {
+            const float4 *src = plane_src(q);
+            for (int idx = threadIdx.x; idx < nzv * nyp; idx += THREADS) {
+                const int j = idx / nyp, sl = idx - j * nyp;
+                const int z = (j - rs + N) % N;
+                const int tile = __fns(ymask, 0, (sl >> 4) + 1);                       // (sl>>4)-th set bit
+                cp_async16(stage + idx, src + (size_t)z * slab + 16 * tile + (sl & 15));
+            }
         }
-        fft_pencil<E>(v, plane + ky, P, t, tw, true);
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cmulf(v[m], f[m]);
-        fft_pencil<E>(v, plane + ky, P, t, tw, true);
-#pragma unroll
-        for (int m = 0; m < E; ++m) plane[(t + 8 * m) * P + ky] = v[m];
-    }
-    __syncthreads();
+        cp_async_commit();
+    };
 
-    // ---- phase 3: inverse y of every row, shared -> global
-    for (int w = warp; w < N / 4; w += NW) {
-        const int z = 32 * (w >> 3) + (w & 7) + 8 * c;
-        float2 v[E];
+    int q = blockIdx.x;          // plane whose phase 1 comes next
+    int qcur = -1;               // plane whose phase 2 is done (phase 3 pending)
+    prefetch_rows(q);
+    for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
+    for (int i = threadIdx.x; i < H; i += THREADS) { twM[i] = twM_g[i]; twh_s[i] = twh_g[i]; }
+
+    while (true) {
+        cp_async_wait<0>();
+        __syncthreads();          // rows of plane q are staged; phase 2 of plane qcur is complete
+        {
+            // ---- row loop: phase 3 of plane qcur (inverse y, shared -> HBM), then phase 1 of plane q
+            //      (forward y of the rows inside the support box, staging -> shared)
+            float2 twr[EM], twh[EM];
 #pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) v[n1] = plane[z * P + t + 8 * n1];
-        fft_pencil<E>(v, plane + z * P, 1, t, tw, true);
+            for (int m = 0; m < EM; ++m) { twr[m] = twM[m * LM + tM]; twh[m] = twh_s[tM + LM * m]; }
+            const TwReg<EM> tw{twr};
+            const float4 *src = q < nplanes ? plane_src(q) : X1;
+            float4 *dst = X2;
+            if (qcur >= 0) {
+                const int kx = qcur % N, vol = (qcur / N) % 3, pair = qcur / (3 * N);
+                dst = X2 + (size_t)(pair * 3 + vol) * N * slab + (size_t)kx * H;       // + z*slab + y/2
+            }
+            for (int w = warp; w < N / GM; w += NW) {
+                const int z = w * GM + gM;
+                if (qcur >= 0) {
+                    C2 v[EM];
 #pragma unroll
-        for (int m = 0; m < E; ++m) dst[(size_t)z * pl + t + 8 * m] = v[m];
+                    for (int n1 = 0; n1 < EM; ++n1) v[n1] = lds_c2(plane + z * P + tM + LM * n1);
+                    fft_row_split2adj<LM, EM>(v, plane + z * P, 1, tM, tw, twh);
+#pragma unroll
+                    for (int m = 0; m < EM; ++m) stg_c2(dst + (size_t)z * slab + tM + LM * m, v[m]);
+                }
+                const int j = (z + rs) % N;
+                const bool act = j < nzv;
+                if (q < nplanes && __any_sync(0xffffffffu, act)) {
+                    C2 v[EM];
+#pragma unroll
+                    for (int n1 = 0; n1 < EM; ++n1) {
+                        const int jj = tM + LM * n1, tile = jj >> 4;                   // y = 2jj, 2jj+1
+                        if (act && ((ymask >> tile) & 1u)) {
+                            if (STAGED) v[n1] = lds_c2(stage + j * nyp + 16 * __popc(ymask & ((1u << tile) - 1u)) + (jj & 15));
+                            else v[n1] = ldg_c2(src + (size_t)z * slab + jj);
+                        } else {
+                            v[n1] = c2_zero();
+                        }
+                    }
+                    fft_row_adj2split<LM, EM>(v, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
+                    if (act) {
+#pragma unroll
+                        for (int m = 0; m < EM; ++m) sts_c2(plane + z * P + tM + LM * m, v[m]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (q >= nplanes) break;
+        prefetch_rows(q + gridDim.x);
+
+        // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs ky, ky+H)
+        {
+            const int kx = q % N, vol = (q / N) % 3;
+            const float4 *Fm = (vol == 2 ? F2pk : Fpk) + (size_t)kx * H * N;           // + ky*N + kz
+            const TwSmem<LN> tw{twN + tN};
+            for (int w = warp; w < H / GN; w += NW) {
+                const int ky = w * GN + gN;
+                C2 v[EN];
+#pragma unroll
+                for (int n1 = 0; n1 < EN; ++n1) {
+                    const int z = tN + LN * n1;
+                    const int sz = z <= N / 2 ? z : z - N;
+                    v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + ky) : c2_zero();
+                }
+                fft_pencil2_mul<LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN);
+                fft_pencil2<LN, EN>(v, plane + ky, P, tN, tw);
+#pragma unroll
+                for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + ky, v[m]);
+            }
+        }
+        qcur = q;
+        q += gridDim.x;
     }
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------- kernel C
@@ -312,13 +301,6 @@ __device__ __forceinline__ void fold_best(int64_t &best, float gcc, float ave, f
         if (key > best) best = key;
     }
 }
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
 
 // One CTA owns a tile of 32 rows (fixed z, 32 consecutive y) and walks a chunk of rotation
 // pairs.  Per pair the three X2 tiles (ave2, ave, gcc) stream through a double-buffered
@@ -370,7 +352,11 @@ fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict_
         const int p = p0 + item / 3, vi = item % 3;
         float2 v[E];
 #pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) v[n1] = tile[(t + 8 * n1) * TP + r];
+        for (int n1 = 0; n1 < E; ++n1) {
+            // rows come in y pairs: (re[y], re[y+1], im[y], im[y+1])
+            const float *e = reinterpret_cast<const float *>(tile + (t + 8 * n1) * TP) + 4 * (r >> 1) + (r & 1);
+            v[n1] = make_float2(e[0], e[2]);
+        }
         fft_pencil<E>(v, tile + r, TP, t, tw, true);
         if (vi == 0) {
 #pragma unroll
@@ -408,16 +394,20 @@ fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------- helpers
-// Fq[kx][ky][kz] = F[kz][ky][kx]
-__global__ void transpose_zx_kernel(const float2 *__restrict__ F, float2 *__restrict__ Fq, int N) {
-    __shared__ float2 tl[32][33];
-    const int ky = blockIdx.z;
+// Fpk[kx][ky][kz] = (re F[kz][ky][kx], re F[kz][ky+N/2][kx], im ..., im ...), ky < N/2: the map
+// spectrum in the column pairing of kernel B's phase 2
+__global__ void pair_transpose_kernel(const float2 *__restrict__ F, float4 *__restrict__ Fpk, int N) {
+    __shared__ float4 tl[32][33];
+    const int ky = blockIdx.z, H = N / 2;
     const int kx0 = blockIdx.x * 32, kz0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y)
-        tl[i][threadIdx.x] = F[((size_t)(kz0 + i) * N + ky) * N + kx0 + threadIdx.x];
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const float2 a = F[((size_t)(kz0 + i) * N + ky) * N + kx0 + threadIdx.x];
+        const float2 b = F[((size_t)(kz0 + i) * N + ky + H) * N + kx0 + threadIdx.x];
+        tl[i][threadIdx.x] = make_float4(a.x, b.x, a.y, b.y);
+    }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y)
-        Fq[((size_t)(kx0 + i) * N + ky) * N + kz0 + threadIdx.x] = tl[threadIdx.x][i];
+        Fpk[((size_t)(kx0 + i) * H + ky) * N + kz0 + threadIdx.x] = tl[threadIdx.x][i];
 }
 
 // max squared distance from voxel 0 (periodic) of any voxel where template or mask is non-zero
@@ -437,12 +427,38 @@ __global__ void support_kernel(const float *__restrict__ tmpl, const float *__re
 }
 
 // ------------------------------------------------------------------------------- host side
-template <int N> static int fused_init_n() {
+// plane + dummy rows + twiddle tables; the rest of the 227 KB is the row staging buffer
+template <int N> static constexpr size_t smem_b_fixed() {
+    return (size_t)((N + 32 / FusedCfg<N>::LM) * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2);
+}
+constexpr size_t kSmemMax = 227 * 1024;
+
+// twiddle table of a LANES x E pencil: entry [k1][t] = exp(+2 pi i t k1 / (LANES E))
+static int upload_pencil_twiddles(int lanes, int e, float2 **out) {
+    std::vector<float2> h((size_t)lanes * e);
+    const double n = (double)lanes * e;
+    for (int t = 0; t < lanes; ++t)
+        for (int k1 = 0; k1 < e; ++k1) {
+            const double a = 2.0 * M_PI * (double)(t * k1) / n;
+            h[(size_t)k1 * lanes + t] = make_float2((float)cos(a), (float)sin(a));
+        }
+    PFB_CUDA(cudaMalloc(out, sizeof(float2) * h.size()));
+    PFB_CUDA(cudaMemcpy(*out, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    return PFB_OK;
+}
+
+template <int N> static int fused_init_n(Plan *p) {
+    using Cfg = FusedCfg<N>;
+    int rc;
+    if ((rc = upload_pencil_twiddles(Cfg::LN, Cfg::EN, &p->twdN))) return rc;
+    if ((rc = upload_pencil_twiddles(Cfg::LM, Cfg::EM, &p->twdM))) return rc;
     constexpr int TP = 33;
     PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256)>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(N * (N + 1) * sizeof(float2))));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * 34 * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t))));
     return PFB_OK;
@@ -451,15 +467,17 @@ template <int N> static int fused_init_n() {
 bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (nx == 64 || nx == 128); }
 
 int fused_init(Plan *p) {
-    if (p->nx == 64) return fused_init_n<64>();
-    return fused_init_n<128>();
+    if (p->nx == 64) return fused_init_n<64>(p);
+    return fused_init_n<128>(p);
 }
 
 int fused_prepare_target(Plan *p, cudaStream_t s) {
     const int N = p->nx;
-    dim3 grid(N / 32, N / 32, N), block(32, 8);
-    { LaunchScope ls(p, KC_OTHER, s); transpose_zx_kernel<<<grid, block, 0, s>>>(p->F, p->Fq, N); }
-    { LaunchScope ls(p, KC_OTHER, s); transpose_zx_kernel<<<grid, block, 0, s>>>(p->F2, p->F2q, N); }
+    dim3 grid(N / 32, N / 32, N / 2), block(32, 8);
+    { LaunchScope ls(p, KC_OTHER, s);
+      pair_transpose_kernel<<<grid, block, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N); }
+    { LaunchScope ls(p, KC_OTHER, s);
+      pair_transpose_kernel<<<grid, block, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N); }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
@@ -507,8 +525,15 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
     }
     {
         LaunchScope ls(p, KC_FUSED_B, s);
-        fused_fftyz_mul_kernel<N, BT><<<dim3(N, 3, npairs), BT, N * (N + 1) * sizeof(float2), s>>>(
-            p->A, p->B, p->Fq, p->F2q, p->tw[0], p->rs, p->ymask, p->nsig);
+        const int nplanes = N * 3 * npairs;
+        const size_t stage_bytes = (size_t)nzv * 16 * nyt * sizeof(float4);
+        const int staged = smem_b_fixed<N>() + stage_bytes <= kSmemMax ? 1 : 0;
+        const size_t smem = smem_b_fixed<N>() + (staged ? stage_bytes : 0);
+        auto kern = staged ? fused_fftyz_mul_kernel<N, BT, true> : fused_fftyz_mul_kernel<N, BT, false>;
+        kern<<<std::min(nplanes, p->sm_count), BT, smem, s>>>(
+            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(p->B),
+            reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
+            p->tw[0], p->rs, p->ymask, p->nsig, nplanes);
     }
     {
         // enough CTAs for ~4 waves: split the pair loop into chunks
