@@ -189,8 +189,11 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     const int nzv = min(2 * rs + 1, N);
     const int nyp = 16 * __popc(ymask);                                                // y pairs per staged row
 
+    // q -> (pair, volume, kx), pair fastest: the planes in flight at any time share their map-spectrum
+    // plane (kx, volume) and the two mask volumes of a pair re-read the same X1 rows back to back
+    const int npairs = nplanes / (3 * N);
     auto plane_src = [&](int q) {
-        const int kx = q % N, vol = (q / N) % 3, pair = q / (3 * N);
+        const int pair = q % npairs, vol = (q / npairs) % 3, kx = q / (3 * npairs);
         const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
         return X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;           // + z*slab + y/2
     };
@@ -226,7 +229,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
             const float4 *src = q < nplanes ? plane_src(q) : X1;
             float4 *dst = X2;
             if (qcur >= 0) {
-                const int kx = qcur % N, vol = (qcur / N) % 3, pair = qcur / (3 * N);
+                const int pair = qcur % npairs, vol = (qcur / npairs) % 3, kx = qcur / (3 * npairs);
                 dst = X2 + (size_t)(pair * 3 + vol) * N * slab + (size_t)kx * H;       // + z*slab + y/2
             }
             for (int w = warp; w < N / GM; w += NW) {
@@ -267,7 +270,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 
         // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs ky, ky+H)
         {
-            const int kx = q % N, vol = (q / N) % 3;
+            const int vol = (q / npairs) % 3, kx = q / (3 * npairs);
             const float4 *Fm = (vol == 2 ? F2pk : Fpk) + (size_t)kx * H * N;           // + ky*N + kz
             const TwSmem<LN> tw{twN + tN};
             for (int w = warp; w < H / GN; w += NW) {
@@ -292,103 +295,115 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 }
 
 // ------------------------------------------------------------------------------- kernel C
-__device__ __forceinline__ void fold_best(int64_t &best, float gcc, float ave, float sd_arg_ave2, float norm,
-                                          uint32_t rot) {
-    const float var = __fsub_rn(__fmul_rn(sd_arg_ave2, norm), __fmul_rn(ave, ave));
-    const float lcc = __fdiv_rn(gcc, __fsqrt_rn(var));
-    if (lcc == lcc) {
-        const int64_t key = pack_best(__float_as_uint(lcc), rot);
-        if (key > best) best = key;
-    }
-}
-
-// One CTA owns a tile of 32 rows (fixed z, 32 consecutive y) and walks a chunk of rotation
-// pairs.  Per pair the three X2 tiles (ave2, ave, gcc) stream through a double-buffered
-// cp.async pipeline; thread (row r, t) transforms its row along x and keeps sqrt(var) of
-// its 16 voxels in registers until the gcc row arrives.  Tile layout [kx][34]: pitch 34
-// keeps 16-byte cp.async destinations aligned and, with the two pencils of a half-warp on
-// adjacent rows, every shared access conflict free.
+// One CTA (128 threads) owns a tile of 32 rows (fixed z, 32 consecutive y = 16 y pairs) and
+// walks a chunk of rotation pairs.  Per pair the three X2 tiles (ave2, ave, gcc) are copied
+// with cp.async into shared memory in exactly the layout kernel B wrote -- [kx][16 y pairs] of
+// float4 -- and eight lanes transform one y PAIR along x as two independent packed pencils.
+// A thread keeps 1/sqrt(var) of its 2 rows x 16 x x 2 rotations in registers until the gcc
+// tile arrives; the running best lives in shared memory and goes to HBM as one atomicMax per
+// voxel per chunk.  The tile is single-buffered: three CTAs per SM overlap each other's loads,
+// and the next tile's copy is issued before the epilogue arithmetic of the current one.
 template <int N>
-__global__ void __launch_bounds__(256, 2)
-fused_ifftx_lcc_kernel(const float2 *__restrict__ X2, const uint8_t *__restrict__ lcc_mask, float norm,
+__global__ void __launch_bounds__(128, 3)
+fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict__ lcc_mask, float norm,
                        int first_index, int count, int pairs_per_chunk, int64_t *__restrict__ best,
-                       const float2 *__restrict__ twN) {
-    constexpr int E = N / 8, TP = 34, BP = N + 1;
-    extern __shared__ float2 smem[];
-    float2 *tiles[2] = {smem, smem + N * TP};
-    int64_t *lbest = reinterpret_cast<int64_t *>(smem + 2 * N * TP);
+                       const float2 *__restrict__ twN_g) {
+    constexpr int E = N / 8, H = N / 2, TP = 17, BP = N + 4;
+    extern __shared__ float4 smem4[];
+    float4 *tile = smem4;                                             // [N][TP]
+    int64_t *lbest = reinterpret_cast<int64_t *>(tile + N * TP);      // [32][BP]
+    float2 *tws = reinterpret_cast<float2 *>(lbest + 32 * BP);        // [E][8] W_N^(t k1)
     const int y0 = 32 * blockIdx.x, z = blockIdx.y;
     const int npairs = (count + 1) / 2;
     const int p0 = blockIdx.z * pairs_per_chunk, p1 = min(npairs, p0 + pairs_per_chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = lane & 7, r = 4 * warp + (lane >> 3);
-    float2 tw[E];
-    load_twiddles<E>(tw, twN, t);
-    const size_t pl = (size_t)N * N;
-    const size_t row = ((size_t)z * N + y0 + r) * N;
-    unsigned mbits = 0;
+    const int t = lane & 7, rp = 4 * warp + (lane >> 3);              // y pair: rows y0+2rp, y0+2rp+1
+    const size_t slab = (size_t)N * H;
+    const size_t rowa = ((size_t)z * N + y0 + 2 * rp) * N, rowb = rowa + N;
+    int64_t *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
+    unsigned ma = 0, mb = 0;
 #pragma unroll
     for (int m = 0; m < E; ++m) {
-        if (lcc_mask[row + t + 8 * m]) mbits |= 1u << m;
-        lbest[r * BP + t + 8 * m] = kBestInit;
+        if (lcc_mask[rowa + t + 8 * m]) ma |= 1u << m;
+        if (lcc_mask[rowb + t + 8 * m]) mb |= 1u << m;
+        lba[8 * m] = kBestInit;
+        lbb[8 * m] = kBestInit;
     }
+    for (int i = threadIdx.x; i < N; i += 128) tws[i] = twN_g[i];
+    const TwSmem<8> tw{tws + t};
     const int nitems = 3 * (p1 - p0);
     auto prefetch = [&](int item) {
         const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
-        const float2 *src = X2 + ((size_t)(p * 3 + vol) * N + z) * pl + y0;
-        float2 *dst = tiles[item & 1];
-        for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
-            const int kx = idx >> 4, ch = idx & 15;
-            cp_async16(dst + kx * TP + 2 * ch, src + (size_t)kx * N + 2 * ch);
+        const float4 *src = X2 + ((size_t)(p * 3 + vol) * N + z) * slab + y0 / 2;
+        for (int idx = threadIdx.x; idx < 16 * N; idx += 128) {
+            const int kx = idx >> 4, c = idx & 15;
+            cp_async16(tile + kx * TP + c, src + (size_t)kx * H + c);
         }
         cp_async_commit();
     };
     if (nitems > 0) prefetch(0);
-    float2 sd[E];
+    C2 sd[E];
+    constexpr int Q = E / 8;
     for (int item = 0; item < nitems; ++item) {
-        if (item + 1 < nitems) { prefetch(item + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        cp_async_wait<0>();
         __syncthreads();
-        float2 *tile = tiles[item & 1];
         const int p = p0 + item / 3, vi = item % 3;
-        float2 v[E];
+        {
+            C2 v[E];
 #pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) {
-            // rows come in y pairs: (re[y], re[y+1], im[y], im[y+1])
-            const float *e = reinterpret_cast<const float *>(tile + (t + 8 * n1) * TP) + 4 * (r >> 1) + (r & 1);
-            v[n1] = make_float2(e[0], e[2]);
+            for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + (t + 8 * n1) * TP + rp);
+            pencil2_stage1<8, E>(v, tile + rp, TP, t, tw);
         }
-        fft_pencil<E>(v, tile + r, TP, t, tw, true);
-        if (vi == 0) {
+        const uint32_t ia = (uint32_t)(first_index + 2 * p);
+        const bool have_b = 2 * p + 1 < count;
 #pragma unroll
-            for (int m = 0; m < E; ++m) sd[m] = v[m];                  // ave2
-        } else if (vi == 1) {
-#pragma unroll
-            for (int m = 0; m < E; ++m) {                              // 1/sqrt(N ave2 - ave^2)
-                // var <= 0 gives inf / NaN exactly where the reference's gcc/sqrt(var) does
-                sd[m].x = rsqrtf(__fsub_rn(__fmul_rn(sd[m].x, norm), __fmul_rn(v[m].x, v[m].x)));
-                sd[m].y = rsqrtf(__fsub_rn(__fmul_rn(sd[m].y, norm), __fmul_rn(v[m].y, v[m].y)));
+        for (int q = 0; q < Q; ++q) {
+            // outputs x = t + 8 m, m = q + Q k0, of this chunk go straight into the epilogue
+            C2 a[8];
+            pencil2_stage2<8>(a, tile + rp, TP, t, q);
+            if (q == Q - 1) {
+                __syncthreads();       // every pencil is out of the tile: refill it while the arithmetic runs
+                if (item + 1 < nitems) prefetch(item + 1);
             }
-        } else {
-            const uint32_t ia = (uint32_t)(first_index + 2 * p);
-            const bool have_b = 2 * p + 1 < count;
 #pragma unroll
-            for (int m = 0; m < E; ++m) {
-                if ((mbits >> m) & 1u) {
-                    int64_t b = lbest[r * BP + t + 8 * m];
-                    const float la = __fmul_rn(v[m].x, sd[m].x), lb = __fmul_rn(v[m].y, sd[m].y);
-                    if (la == la) { const int64_t k = pack_best(__float_as_uint(la), ia); if (k > b) b = k; }
-                    if (have_b && lb == lb) { const int64_t k = pack_best(__float_as_uint(lb), ia + 1); if (k > b) b = k; }
-                    lbest[r * BP + t + 8 * m] = b;
+            for (int k0 = 0; k0 < 8; ++k0) {
+                const int m = q + Q * k0;
+                if (vi == 0) {
+                    sd[m] = a[k0];                                     // ave2
+                } else if (vi == 1) {                                  // 1/sqrt(N ave2 - ave^2)
+                    // var <= 0 gives inf / NaN exactly where the reference's gcc/sqrt(var) does
+                    const float2 vr = psub(pmul(sd[m].re, pdup(norm)), pmul(a[k0].re, a[k0].re));
+                    const float2 vq = psub(pmul(sd[m].im, pdup(norm)), pmul(a[k0].im, a[k0].im));
+                    sd[m].re = make_float2(rsqrtf(vr.x), rsqrtf(vr.y));
+                    sd[m].im = make_float2(rsqrtf(vq.x), rsqrtf(vq.y));
+                } else {
+                    // (row a, row b) of rotation a / rotation b
+                    const float2 la = pmul(a[k0].re, sd[m].re), lb = pmul(a[k0].im, sd[m].im);
+                    if ((ma >> m) & 1u) {
+                        int64_t b = lba[8 * m];
+                        if (la.x == la.x) { const int64_t k = pack_best(__float_as_uint(la.x), ia); if (k > b) b = k; }
+                        if (have_b && lb.x == lb.x) { const int64_t k = pack_best(__float_as_uint(lb.x), ia + 1); if (k > b) b = k; }
+                        lba[8 * m] = b;
+                    }
+                    if ((mb >> m) & 1u) {
+                        int64_t b = lbb[8 * m];
+                        if (la.y == la.y) { const int64_t k = pack_best(__float_as_uint(la.y), ia); if (k > b) b = k; }
+                        if (have_b && lb.y == lb.y) { const int64_t k = pack_best(__float_as_uint(lb.y), ia + 1); if (k > b) b = k; }
+                        lbb[8 * m] = b;
+                    }
                 }
             }
         }
-        __syncthreads();       // everyone is done with this buffer before it is refilled
     }
 #pragma unroll
     for (int m = 0; m < E; ++m) {
-        if ((mbits >> m) & 1u) {
-            const int64_t b = lbest[r * BP + t + 8 * m];
-            if (b > kBestInit) atomicMax(reinterpret_cast<long long *>(best + row + t + 8 * m), (long long)b);
+        if ((ma >> m) & 1u) {
+            const int64_t b = lba[8 * m];
+            if (b > kBestInit) atomicMax(reinterpret_cast<long long *>(best + rowa + t + 8 * m), (long long)b);
+        }
+        if ((mb >> m) & 1u) {
+            const int64_t b = lbb[8 * m];
+            if (b > kBestInit) atomicMax(reinterpret_cast<long long *>(best + rowb + t + 8 * m), (long long)b);
         }
     }
 }
@@ -432,6 +447,9 @@ template <int N> static constexpr size_t smem_b_fixed() {
     return (size_t)((N + 32 / FusedCfg<N>::LM) * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2);
 }
 constexpr size_t kSmemMax = 227 * 1024;
+template <int N> static constexpr size_t smem_c() {
+    return (size_t)N * 17 * sizeof(float4) + (size_t)32 * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
+}
 
 // twiddle table of a LANES x E pencil: entry [k1][t] = exp(+2 pi i t k1 / (LANES E))
 static int upload_pencil_twiddles(int lanes, int e, float2 **out) {
@@ -460,7 +478,7 @@ template <int N> static int fused_init_n(Plan *p) {
     PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * N * 34 * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t))));
+                                  (int)smem_c<N>()));
     return PFB_OK;
 }
 
@@ -536,15 +554,15 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
             p->tw[0], p->rs, p->ymask, p->nsig, nplanes);
     }
     {
-        // enough CTAs for ~4 waves: split the pair loop into chunks
+        // enough CTAs for ~4 waves of 3 CTAs per SM: split the pair loop into chunks
         const int tiles = (N / 32) * N;
-        int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * 2 + tiles - 1) / tiles));
+        int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * 3 + tiles - 1) / tiles));
         const int ppc = (npairs + chunks - 1) / chunks;
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
-        fused_ifftx_lcc_kernel<N><<<dim3(N / 32, N, chunks), 256,
-                                    2 * N * 34 * sizeof(float2) + 32 * (N + 1) * sizeof(int64_t), s>>>(
-            p->B, p->lcc_mask, p->norm_factor, rot_index_offset + first, count, ppc, best, p->tw[0]);
+        fused_ifftx_lcc_kernel<N><<<dim3(N / 32, N, chunks), 128, smem_c<N>(), s>>>(
+            reinterpret_cast<const float4 *>(p->B), p->lcc_mask, p->norm_factor, rot_index_offset + first, count, ppc,
+            best, p->twdN);
     }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
