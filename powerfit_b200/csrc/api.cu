@@ -156,6 +156,7 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     if (p->fused) {
         PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
+        PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 8);
     }
 #undef PFB_ALLOC
     if ((rc = ensure_rot_capacity(p, 1024))) return fail(rc);
@@ -169,7 +170,7 @@ int pfb_plan_destroy(pfb_plan *h) {
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM};
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     delete h;

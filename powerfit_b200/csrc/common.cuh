@@ -102,6 +102,7 @@ struct Plan {
     bool fused = false;
     float2 *Fq = nullptr, *F2q = nullptr;
     float2 *twdN = nullptr, *twdM = nullptr;       // packed-pencil twiddle tables [k1][t] (fft_core.cuh)
+    uint32_t *mbits = nullptr;                     // lcc_mask bit-packed in kernel C's lane layout
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]

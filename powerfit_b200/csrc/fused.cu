@@ -153,6 +153,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
 
+constexpr int kThreadsB = 512;      // kernel B: 16 warps x 128 registers (256 x 255 measured 3 % slower)
 template <int N> struct FusedCfg;
 template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8; };
 template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8; };
@@ -303,15 +304,15 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 // tile arrives; the running best lives in shared memory and goes to HBM as one atomicMax per
 // voxel per chunk.  The tile is single-buffered: three CTAs per SM overlap each other's loads,
 // and the next tile's copy is issued before the epilogue arithmetic of the current one.
-template <int N>
-__global__ void __launch_bounds__(128, 3)
-fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict__ lcc_mask, float norm,
+template <int N, int NBUF>
+__global__ void __launch_bounds__(128, NBUF == 1 ? 3 : 2)
+fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict__ mbits, float norm,
                        int first_index, int count, int pairs_per_chunk, int64_t *__restrict__ best,
                        const float2 *__restrict__ twN_g) {
     constexpr int E = N / 8, H = N / 2, TP = 17, BP = N + 4;
     extern __shared__ float4 smem4[];
-    float4 *tile = smem4;                                             // [N][TP]
-    int64_t *lbest = reinterpret_cast<int64_t *>(tile + N * TP);      // [32][BP]
+    float4 *tile0 = smem4;                                            // [NBUF][N][TP]
+    int64_t *lbest = reinterpret_cast<int64_t *>(tile0 + NBUF * N * TP);   // [32][BP]
     float2 *tws = reinterpret_cast<float2 *>(lbest + 32 * BP);        // [E][8] W_N^(t k1)
     const int y0 = 32 * blockIdx.x, z = blockIdx.y;
     const int npairs = (count + 1) / 2;
@@ -321,11 +322,10 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict_
     const size_t slab = (size_t)N * H;
     const size_t rowa = ((size_t)z * N + y0 + 2 * rp) * N, rowb = rowa + N;
     int64_t *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
-    unsigned ma = 0, mb = 0;
+    // bit m of a row's word t: lcc_mask at x = t + 8 m (built once per target by mask_bits_kernel)
+    const unsigned ma = mbits[((size_t)z * N + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * N + y0 + 2 * rp + 1) * 8 + t];
 #pragma unroll
     for (int m = 0; m < E; ++m) {
-        if (lcc_mask[rowa + t + 8 * m]) ma |= 1u << m;
-        if (lcc_mask[rowb + t + 8 * m]) mb |= 1u << m;
         lba[8 * m] = kBestInit;
         lbb[8 * m] = kBestInit;
     }
@@ -335,6 +335,7 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict_
     auto prefetch = [&](int item) {
         const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
         const float4 *src = X2 + ((size_t)(p * 3 + vol) * N + z) * slab + y0 / 2;
+        float4 *tile = tile0 + (item % NBUF) * N * TP;
         for (int idx = threadIdx.x; idx < 16 * N; idx += 128) {
             const int kx = idx >> 4, c = idx & 15;
             cp_async16(tile + kx * TP + c, src + (size_t)kx * H + c);
@@ -345,8 +346,14 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict_
     C2 sd[E];
     constexpr int Q = E / 8;
     for (int item = 0; item < nitems; ++item) {
-        cp_async_wait<0>();
+        if (NBUF == 2) {
+            // the other buffer was released by the barrier at the end of the previous item
+            if (item + 1 < nitems) { prefetch(item + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
+        float4 *tile = tile0 + (item % NBUF) * N * TP;
         const int p = p0 + item / 3, vi = item % 3;
         {
             C2 v[E];
@@ -361,7 +368,7 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict_
             // outputs x = t + 8 m, m = q + Q k0, of this chunk go straight into the epilogue
             C2 a[8];
             pencil2_stage2<8>(a, tile + rp, TP, t, q);
-            if (q == Q - 1) {
+            if (q == Q - 1 && NBUF == 1) {
                 __syncthreads();       // every pencil is out of the tile: refill it while the arithmetic runs
                 if (item + 1 < nitems) prefetch(item + 1);
             }
@@ -394,6 +401,7 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint8_t *__restrict_
                 }
             }
         }
+        if (NBUF == 2) __syncthreads();   // this item's tile may be refilled by the next iteration's prefetch
     }
 #pragma unroll
     for (int m = 0; m < E; ++m) {
@@ -425,6 +433,18 @@ __global__ void pair_transpose_kernel(const float2 *__restrict__ F, float4 *__re
         Fpk[((size_t)(kx0 + i) * H + ky) * N + kz0 + threadIdx.x] = tl[threadIdx.x][i];
 }
 
+// mbits[row * 8 + t], row = z*N + y: bit m = (lcc_mask[row][t + 8 m] != 0) -- kernel C's lane layout
+__global__ void mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint32_t *__restrict__ mbits, int N, long rows) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 8) return;
+    const long row = i >> 3;
+    const int t = (int)(i & 7);
+    uint32_t w = 0;
+    for (int m = 0; m < N / 8; ++m)
+        if (lcc_mask[row * N + t + 8 * m]) w |= 1u << m;
+    mbits[i] = w;
+}
+
 // max squared distance from voxel 0 (periodic) of any voxel where template or mask is non-zero
 __global__ void support_kernel(const float *__restrict__ tmpl, const float *__restrict__ mask, int nz, int ny,
                                int nx, int *out) {
@@ -447,8 +467,8 @@ template <int N> static constexpr size_t smem_b_fixed() {
     return (size_t)((N + 32 / FusedCfg<N>::LM) * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2);
 }
 constexpr size_t kSmemMax = 227 * 1024;
-template <int N> static constexpr size_t smem_c() {
-    return (size_t)N * 17 * sizeof(float4) + (size_t)32 * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
+template <int N> static constexpr size_t smem_c(int nbuf) {
+    return (size_t)nbuf * N * 17 * sizeof(float4) + (size_t)32 * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
 }
 
 // twiddle table of a LANES x E pencil: entry [k1][t] = exp(+2 pi i t k1 / (LANES E))
@@ -473,12 +493,14 @@ template <int N> static int fused_init_n(Plan *p) {
     constexpr int TP = 33;
     PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), true>,
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, kThreadsB, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), false>,
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, kThreadsB, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c<N>(1)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c<N>(2)));
     return PFB_OK;
 }
 
@@ -496,6 +518,9 @@ int fused_prepare_target(Plan *p, cudaStream_t s) {
       pair_transpose_kernel<<<grid, block, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N); }
     { LaunchScope ls(p, KC_OTHER, s);
       pair_transpose_kernel<<<grid, block, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N); }
+    { LaunchScope ls(p, KC_OTHER, s);
+      const long rows = (long)N * N;
+      mask_bits_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, N, rows); }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
@@ -532,7 +557,7 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
 template <int N>
 static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s) {
     constexpr int TP = 33;
-    constexpr int BT = N >= 128 ? 512 : 256;
+    constexpr int BT = kThreadsB;
     const int npairs = (count + 1) / 2;
     const int nzv = std::min(2 * p->rs + 1, N);
     const int nyt = __builtin_popcount(p->ymask);
@@ -560,8 +585,10 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
         const int ppc = (npairs + chunks - 1) / chunks;
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
-        fused_ifftx_lcc_kernel<N><<<dim3(N / 32, N, chunks), 128, smem_c<N>(), s>>>(
-            reinterpret_cast<const float4 *>(p->B), p->lcc_mask, p->norm_factor, rot_index_offset + first, count, ppc,
+        static const int nbuf = getenv("PFB_C_NBUF") ? atoi(getenv("PFB_C_NBUF")) : 1;
+        auto kern = nbuf == 2 ? fused_ifftx_lcc_kernel<N, 2> : fused_ifftx_lcc_kernel<N, 1>;
+        kern<<<dim3(N / 32, N, chunks), 128, smem_c<N>(nbuf == 2 ? 2 : 1), s>>>(
+            reinterpret_cast<const float4 *>(p->B), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
             best, p->twdN);
     }
     PFB_CUDA(cudaGetLastError());
