@@ -228,6 +228,8 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    if world > 1:
+        dist.barrier()          # rank 0 started the clock sampler: line the ranks up again before timing
     launches0 = corr.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)

@@ -120,10 +120,11 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     DeviceGuard guard(device);
     if (!guard.ok) { delete h; set_error("cudaSetDevice failed"); return PFB_ERR_CUDA; }
     if (max_batch <= 0) {
-        // default: as many rotations in flight as fit ~1.5 GB of work buffers, 2..32
+        // default: as many rotations in flight as fit ~4 GB of work buffers, 2..64 (measured at 128^3:
+        // 32 -> 41.0k, 48 -> 41.8k, 64 -> 42.3k rotations/s; longer launches amortise tails and prologues)
         const long per_pair = 6L * p->V * (long)sizeof(float2);
-        long pairs = (1536L << 20) / per_pair;
-        pairs = std::max(1L, std::min(16L, pairs));
+        long pairs = (4096L << 20) / per_pair;
+        pairs = std::max(1L, std::min(32L, pairs));
         max_batch = (int)(2 * pairs);
     }
     if (const char *e = getenv("PFB_BATCH")) max_batch = std::max(1, atoi(e));

@@ -582,7 +582,9 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
         // enough CTAs for ~4 waves of 3 CTAs per SM: split the pair loop into chunks
         const int tiles = (N / 32) * N;
         int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * 3 + tiles - 1) / tiles));
-        const int ppc = (npairs + chunks - 1) / chunks;
+        int ppc = (npairs + chunks - 1) / chunks;
+        static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
+        if (ppc_env > 0) ppc = ppc_env;
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
         static const int nbuf = getenv("PFB_C_NBUF") ? atoi(getenv("PFB_C_NBUF")) : 1;
