@@ -85,6 +85,8 @@ int fused_init(Plan *p);
 int fused_prepare_target(Plan *p, cudaStream_t s);
 int fused_prepare_template(Plan *p, cudaStream_t s);
 int fused_batch(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s);
+int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s);
+int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
 
 struct Plan {
     int nz = 0, ny = 0, nx = 0, rmax = 0, device = 0;
@@ -107,6 +109,13 @@ struct Plan {
     unsigned ymask = 0;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]
     float2 *B = nullptr;                           // product / inverse work: [batch/2][3][V]
+    // fused path, overlapped mode: kernel C of batch n runs on a second stream next to kernels A and
+    // B of batch n+1 (B leaves shared-memory / issue slots idle, C is latency bound), X2 double-buffered
+    float2 *B2 = nullptr;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t evB[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr};
+    bool overlap = false;
+    int b_threads = 512;                           // kernel B CTA size (512, or 256 to leave room for C)
     double *rot_dev = nullptr;
     long rot_cap = 0;
     int64_t *best_scratch = nullptr;              // used by pfb_search_host

@@ -153,19 +153,18 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
 
-constexpr int kThreadsB = 512;      // kernel B: 16 warps x 128 registers (256 x 255 measured 3 % slower)
 template <int N> struct FusedCfg;
 template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8; };
 template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8; };
 
 // Persistent: one CTA per SM walks the (kx, volume, pair) planes q = blockIdx.x, + gridDim.x, ...
-// While a plane is in phase 2, cp.async pulls the support rows of the CTA's NEXT plane into a
-// staging buffer; the row loop then does phase 3 of the current plane and phase 1 of the next
-// one row by row (a row's storage is free for the next plane the moment its inverse transform
-// has left for HBM), so there are two block barriers per plane, phase 1 never waits on HBM and
-// nothing drains between planes.  `staged` = 0 (support box too large for the staging buffer)
-// falls back to direct loads in phase 1.
-template <int N, int THREADS, bool STAGED>
+// The row loop does phase 3 of the current plane and phase 1 of the CTA's next plane row by row
+// (a row's storage is free for the next plane the moment its inverse transform has left for
+// HBM), so there are two block barriers per plane and nothing drains between planes.  Measured
+// alternatives: staging the next plane's rows in shared memory with cp.async is 4 % slower, and
+// fetching them into registers before the inverse transform 20 % slower (register pressure) --
+// the kernel is bound by shared-memory bandwidth, not by load latency.
+template <int N, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fpk,
                        const float4 *__restrict__ F2pk, const float2 *__restrict__ twN_g,
@@ -182,52 +181,35 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     float2 *twN = reinterpret_cast<float2 *>(dummy + GM * P);     // [EN][LN] W_N^(t k1)
     float2 *twM = twN + N;                                        // [EM][LM] W_H^(t k1)
     float2 *twh_s = twM + H;                                      // [H] W_N^k of the split radix-2 step
-    float4 *stage = reinterpret_cast<float4 *>(twh_s + H);        // [nzv][nyp] support rows of the next plane
     const size_t slab = (size_t)N * H;                                                 // float4 per z
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tM = lane & (LM - 1), gM = lane / LM;
     const int tN = lane & (LN - 1), gN = lane / LN;
     const int nzv = min(2 * rs + 1, N);
-    const int nyp = 16 * __popc(ymask);                                                // y pairs per staged row
-
     // q -> (pair, volume, kx), pair fastest: the planes in flight at any time share their map-spectrum
     // plane (kx, volume) and the two mask volumes of a pair re-read the same X1 rows back to back
     const int npairs = nplanes / (3 * N);
-    auto plane_src = [&](int q) {
-        const int pair = q % npairs, vol = (q / npairs) % 3, kx = q / (3 * npairs);
-        const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
-        return X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;           // + z*slab + y/2
-    };
-    auto prefetch_rows = [&](int q) {
-        if (STAGED && q < nplanes) {
-            const float4 *src = plane_src(q);
-            for (int idx = threadIdx.x; idx < nzv * nyp; idx += THREADS) {
-                const int j = idx / nyp, sl = idx - j * nyp;
-                const int z = (j - rs + N) % N;
-                const int tile = __fns(ymask, 0, (sl >> 4) + 1);                       // (sl>>4)-th set bit
-                cp_async16(stage + idx, src + (size_t)z * slab + 16 * tile + (sl & 15));
-            }
-        }
-        cp_async_commit();
-    };
 
     int q = blockIdx.x;          // plane whose phase 1 comes next
     int qcur = -1;               // plane whose phase 2 is done (phase 3 pending)
-    prefetch_rows(q);
     for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
     for (int i = threadIdx.x; i < H; i += THREADS) { twM[i] = twM_g[i]; twh_s[i] = twh_g[i]; }
 
     while (true) {
-        cp_async_wait<0>();
-        __syncthreads();          // rows of plane q are staged; phase 2 of plane qcur is complete
+        __syncthreads();          // phase 2 of plane qcur is complete (first pass: the tables are in place)
         {
             // ---- row loop: phase 3 of plane qcur (inverse y, shared -> HBM), then phase 1 of plane q
-            //      (forward y of the rows inside the support box, staging -> shared)
+            //      (forward y of the rows inside the support box, HBM -> shared)
             float2 twr[EM], twh[EM];
 #pragma unroll
             for (int m = 0; m < EM; ++m) { twr[m] = twM[m * LM + tM]; twh[m] = twh_s[tM + LM * m]; }
             const TwReg<EM> tw{twr};
-            const float4 *src = q < nplanes ? plane_src(q) : X1;
+            const float4 *src = X1;
+            if (q < nplanes) {
+                const int pair = q % npairs, vol = (q / npairs) % 3, kx = q / (3 * npairs);
+                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+                src = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;    // + z*slab + y/2
+            }
             float4 *dst = X2;
             if (qcur >= 0) {
                 const int pair = qcur % npairs, vol = (qcur / npairs) % 3, kx = qcur / (3 * npairs);
@@ -235,6 +217,8 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
             }
             for (int w = warp; w < N / GM; w += NW) {
                 const int z = w * GM + gM;
+                const bool act = q < nplanes && (z + rs) % N < nzv;
+                const bool any = __any_sync(0xffffffffu, act);
                 if (qcur >= 0) {
                     C2 v[EM];
 #pragma unroll
@@ -243,31 +227,25 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 #pragma unroll
                     for (int m = 0; m < EM; ++m) stg_c2(dst + (size_t)z * slab + tM + LM * m, v[m]);
                 }
-                const int j = (z + rs) % N;
-                const bool act = j < nzv;
-                if (q < nplanes && __any_sync(0xffffffffu, act)) {
-                    C2 v[EM];
+                C2 vn[EM];                                                             // next plane's row z
+                if (any) {
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) {
-                        const int jj = tM + LM * n1, tile = jj >> 4;                   // y = 2jj, 2jj+1
-                        if (act && ((ymask >> tile) & 1u)) {
-                            if (STAGED) v[n1] = lds_c2(stage + j * nyp + 16 * __popc(ymask & ((1u << tile) - 1u)) + (jj & 15));
-                            else v[n1] = ldg_c2(src + (size_t)z * slab + jj);
-                        } else {
-                            v[n1] = c2_zero();
-                        }
+                        const int jj = tM + LM * n1;                                   // y = 2jj, 2jj+1
+                        vn[n1] = (act && ((ymask >> (jj >> 4)) & 1u)) ? ldg_c2(src + (size_t)z * slab + jj) : c2_zero();
                     }
-                    fft_row_adj2split<LM, EM>(v, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
+                }
+                if (any) {
+                    fft_row_adj2split<LM, EM>(vn, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
                     if (act) {
 #pragma unroll
-                        for (int m = 0; m < EM; ++m) sts_c2(plane + z * P + tM + LM * m, v[m]);
+                        for (int m = 0; m < EM; ++m) sts_c2(plane + z * P + tM + LM * m, vn[m]);
                     }
                 }
             }
         }
         __syncthreads();
         if (q >= nplanes) break;
-        prefetch_rows(q + gridDim.x);
 
         // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs ky, ky+H)
         {
@@ -292,7 +270,6 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
         qcur = q;
         q += gridDim.x;
     }
-    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------- kernel C
@@ -462,11 +439,10 @@ __global__ void support_kernel(const float *__restrict__ tmpl, const float *__re
 }
 
 // ------------------------------------------------------------------------------- host side
-// plane + dummy rows + twiddle tables; the rest of the 227 KB is the row staging buffer
-template <int N> static constexpr size_t smem_b_fixed() {
+// plane + dummy rows + twiddle tables
+template <int N> static constexpr size_t smem_b() {
     return (size_t)((N + 32 / FusedCfg<N>::LM) * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2);
 }
-constexpr size_t kSmemMax = 227 * 1024;
 template <int N> static constexpr size_t smem_c(int nbuf) {
     return (size_t)nbuf * N * 17 * sizeof(float4) + (size_t)32 * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
 }
@@ -493,10 +469,11 @@ template <int N> static int fused_init_n(Plan *p) {
     constexpr int TP = 33;
     PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, kThreadsB, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, kThreadsB, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b<N>()));
+    if (N >= 128)
+        PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_b<N>()));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_c<N>(1)));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -554,10 +531,10 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
     return PFB_OK;
 }
 
-template <int N>
-static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s) {
+// front half of a batch: A (rotate + x) and B (y, z, multiply, z, y) into the work buffer X2
+template <int N, int BT>
+static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
     constexpr int TP = 33;
-    constexpr int BT = kThreadsB;
     const int npairs = (count + 1) / 2;
     const int nzv = std::min(2 * p->rs + 1, N);
     const int nyt = __builtin_popcount(p->ymask);
@@ -569,15 +546,20 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
     {
         LaunchScope ls(p, KC_FUSED_B, s);
         const int nplanes = N * 3 * npairs;
-        const size_t stage_bytes = (size_t)nzv * 16 * nyt * sizeof(float4);
-        const int staged = smem_b_fixed<N>() + stage_bytes <= kSmemMax ? 1 : 0;
-        const size_t smem = smem_b_fixed<N>() + (staged ? stage_bytes : 0);
-        auto kern = staged ? fused_fftyz_mul_kernel<N, BT, true> : fused_fftyz_mul_kernel<N, BT, false>;
-        kern<<<std::min(nplanes, p->sm_count), BT, smem, s>>>(
-            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(p->B),
+        fused_fftyz_mul_kernel<N, BT><<<std::min(nplanes, p->sm_count), BT, smem_b<N>(), s>>>(
+            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
             reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
             p->tw[0], p->rs, p->ymask, p->nsig, nplanes);
     }
+    PFB_CUDA(cudaGetLastError());
+    return PFB_OK;
+}
+
+// back half: C (inverse x, LCC, running best) out of the work buffer X2
+template <int N>
+static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2,
+                        cudaStream_t s) {
+    const int npairs = (count + 1) / 2;
     {
         // enough CTAs for ~4 waves of 3 CTAs per SM: split the pair loop into chunks
         const int tiles = (N / 32) * N;
@@ -590,16 +572,28 @@ static int fused_batch_n(Plan *p, int first, int count, int rot_index_offset, in
         static const int nbuf = getenv("PFB_C_NBUF") ? atoi(getenv("PFB_C_NBUF")) : 1;
         auto kern = nbuf == 2 ? fused_ifftx_lcc_kernel<N, 2> : fused_ifftx_lcc_kernel<N, 1>;
         kern<<<dim3(N / 32, N, chunks), 128, smem_c<N>(nbuf == 2 ? 2 : 1), s>>>(
-            reinterpret_cast<const float4 *>(p->B), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
+            reinterpret_cast<const float4 *>(X2), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
             best, p->twdN);
     }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
+int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
+    if (p->nx == 64) return fused_front_n<64, 256>(p, first, count, X2, s);
+    if (p->b_threads == 256) return fused_front_n<128, 256>(p, first, count, X2, s);
+    return fused_front_n<128, 512>(p, first, count, X2, s);
+}
+
+int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
+    if (p->nx == 64) return fused_back_n<64>(p, first, count, rot_index_offset, best, X2, s);
+    return fused_back_n<128>(p, first, count, rot_index_offset, best, X2, s);
+}
+
 int fused_batch(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s) {
-    if (p->nx == 64) return fused_batch_n<64>(p, first, count, rot_index_offset, best, s);
-    return fused_batch_n<128>(p, first, count, rot_index_offset, best, s);
+    int rc = fused_front(p, first, count, p->B, s);
+    if (rc) return rc;
+    return fused_back(p, first, count, rot_index_offset, best, p->B, s);
 }
 
 }  // namespace pfb
