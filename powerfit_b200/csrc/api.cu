@@ -158,6 +158,7 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
         PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
         PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 8);
+        PFB_ALLOC(p->tmplq, sizeof(float4) * p->V);
         if (const char *e = getenv("PFB_OVERLAP")) p->overlap = atoi(e) != 0;
         if (const char *e = getenv("PFB_B_THREADS")) p->b_threads = atoi(e) == 256 ? 256 : 512;
         if (p->overlap) {
@@ -181,7 +182,7 @@ int pfb_plan_destroy(pfb_plan *h) {
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->B2};
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->B2, p->tmplq};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (int i = 0; i < 2; ++i) {

@@ -104,6 +104,7 @@ struct Plan {
     bool fused = false;
     float2 *Fq = nullptr, *F2q = nullptr;
     float2 *twdN = nullptr, *twdM = nullptr;       // packed-pencil twiddle tables [k1][t] (fft_core.cuh)
+    float4 *tmplq = nullptr;                       // template corner table for kernel A's gather
     uint32_t *mbits = nullptr;                     // lcc_mask bit-packed in kernel C's lane layout
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;

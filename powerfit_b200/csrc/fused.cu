@@ -36,7 +36,7 @@ namespace pfb {
 // ------------------------------------------------------------------------------- kernel A
 template <int N>
 __global__ void __launch_bounds__(256)
-fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict__ mask,
+fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ mask,
                          const double *__restrict__ rot, int first, int count, int nsig,
                          float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
                          unsigned ymask, int nzv) {
@@ -74,11 +74,11 @@ fused_rotate_fftx_kernel(const float *__restrict__ tmpl, const float *__restrict
         if (ox * ox + oy * oy + oz * oz <= lim2) {
             float2 tv = make_float2(0.f, 0.f), mv = make_float2(0.f, 0.f);
             const SrcCoord ca = source_coord(Ra, ox, oy, oz);
-            tv.x = sample_trilinear(tmpl, d, ca);
+            tv.x = sample_trilinear_q(tmplq, d, ca);
             mv.x = sample_nearest(mask, d, ca);
             if (have_b) {
                 const SrcCoord cb = source_coord(Rb, ox, oy, oz);
-                tv.y = sample_trilinear(tmpl, d, cb);
+                tv.y = sample_trilinear_q(tmplq, d, cb);
                 mv.y = sample_nearest(mask, d, cb);
             }
             const int x = ox < 0 ? ox + N : ox;
@@ -422,6 +422,17 @@ __global__ void mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint32_t 
     mbits[i] = w;
 }
 
+// corner table of the template for kernel A's trilinear gather (rotate_device.cuh: sample_trilinear_q)
+__global__ void corner_table_kernel(const float *__restrict__ g, float4 *__restrict__ q, int nz, int ny, int nx) {
+    const long V = (long)nz * ny * nx;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(v % nx), y = (int)((v / nx) % ny);
+        const long zrow = v / ((long)nx * ny) * ny;
+        const int x1 = x + 1 == nx ? 0 : x + 1, y1 = y + 1 == ny ? 0 : y + 1;
+        q[v] = make_float4(g[(zrow + y) * nx + x], g[(zrow + y) * nx + x1], g[(zrow + y1) * nx + x], g[(zrow + y1) * nx + x1]);
+    }
+}
+
 // max squared distance from voxel 0 (periodic) of any voxel where template or mask is non-zero
 __global__ void support_kernel(const float *__restrict__ tmpl, const float *__restrict__ mask, int nz, int ny,
                                int nx, int *out) {
@@ -509,6 +520,8 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
     PFB_CUDA(cudaMemcpyAsync(d_r2, &init, sizeof(int), cudaMemcpyHostToDevice, s));
     { LaunchScope ls(p, KC_OTHER, s);
       support_kernel<<<p->sm_count * 4, 256, 0, s>>>(p->tmpl, p->mask, p->nz, p->ny, p->nx, d_r2); }
+    { LaunchScope ls(p, KC_OTHER, s);
+      corner_table_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->tmpl, p->tmplq, p->nz, p->ny, p->nx); }
     int r2 = -1;
     PFB_CUDA(cudaMemcpyAsync(&r2, d_r2, sizeof(int), cudaMemcpyDeviceToHost, s));
     PFB_CUDA(cudaStreamSynchronize(s));
@@ -541,7 +554,7 @@ static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t
     {
         LaunchScope ls(p, KC_FUSED_A, s);
         fused_rotate_fftx_kernel<N><<<dim3(nzv * nyt, npairs), 256, 2 * N * TP * sizeof(float2), s>>>(
-            p->tmpl, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->ymask, nzv);
+            p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->ymask, nzv);
     }
     {
         LaunchScope ls(p, KC_FUSED_B, s);
