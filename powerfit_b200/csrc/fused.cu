@@ -289,7 +289,9 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
     constexpr int E = N / 8, H = N / 2, TP = 17, BP = N + 4;
     extern __shared__ float4 smem4[];
     float4 *tile0 = smem4;                                            // [NBUF][N][TP]
-    int64_t *lbest = reinterpret_cast<int64_t *>(tile0 + NBUF * N * TP);   // [32][BP]
+    // running best of the chunk as (LCC, rotation) pairs: rotations arrive in increasing order, so a
+    // strict float '>' against a +0.0 start is exactly the packed-key order (common.cuh)
+    float2 *lbest = reinterpret_cast<float2 *>(tile0 + NBUF * N * TP);     // [32][BP] (lcc, rot index bits)
     float2 *tws = reinterpret_cast<float2 *>(lbest + 32 * BP);        // [E][8] W_N^(t k1)
     const int y0 = 32 * blockIdx.x, z = blockIdx.y;
     const int npairs = (count + 1) / 2;
@@ -298,13 +300,13 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
     const int t = lane & 7, rp = 4 * warp + (lane >> 3);              // y pair: rows y0+2rp, y0+2rp+1
     const size_t slab = (size_t)N * H;
     const size_t rowa = ((size_t)z * N + y0 + 2 * rp) * N, rowb = rowa + N;
-    int64_t *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
+    float2 *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
     // bit m of a row's word t: lcc_mask at x = t + 8 m (built once per target by mask_bits_kernel)
     const unsigned ma = mbits[((size_t)z * N + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * N + y0 + 2 * rp + 1) * 8 + t];
 #pragma unroll
     for (int m = 0; m < E; ++m) {
-        lba[8 * m] = kBestInit;
-        lbb[8 * m] = kBestInit;
+        lba[8 * m] = make_float2(0.f, 0.f);
+        lbb[8 * m] = make_float2(0.f, 0.f);
     }
     for (int i = threadIdx.x; i < N; i += 128) tws[i] = twN_g[i];
     const TwSmem<8> tw{tws + t};
@@ -363,18 +365,13 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
                 } else {
                     // (row a, row b) of rotation a / rotation b
                     const float2 la = pmul(a[k0].re, sd[m].re), lb = pmul(a[k0].im, sd[m].im);
-                    if ((ma >> m) & 1u) {
-                        int64_t b = lba[8 * m];
-                        if (la.x == la.x) { const int64_t k = pack_best(__float_as_uint(la.x), ia); if (k > b) b = k; }
-                        if (have_b && lb.x == lb.x) { const int64_t k = pack_best(__float_as_uint(lb.x), ia + 1); if (k > b) b = k; }
-                        lba[8 * m] = b;
-                    }
-                    if ((mb >> m) & 1u) {
-                        int64_t b = lbb[8 * m];
-                        if (la.y == la.y) { const int64_t k = pack_best(__float_as_uint(la.y), ia); if (k > b) b = k; }
-                        if (have_b && lb.y == lb.y) { const int64_t k = pack_best(__float_as_uint(lb.y), ia + 1); if (k > b) b = k; }
-                        lbb[8 * m] = b;
-                    }
+                    // best of the pair first (ties and NaN: rotation a, the lower index, stays)
+                    const bool sa = have_b && (lb.x > la.x || !(la.x == la.x));
+                    const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
+                    const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
+                    const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
+                    if (((ma >> m) & 1u) && ca > lba[8 * m].x) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
+                    if (((mb >> m) & 1u) && cb > lbb[8 * m].x) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
                 }
             }
         }
@@ -383,12 +380,16 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
 #pragma unroll
     for (int m = 0; m < E; ++m) {
         if ((ma >> m) & 1u) {
-            const int64_t b = lba[8 * m];
-            if (b > kBestInit) atomicMax(reinterpret_cast<long long *>(best + rowa + t + 8 * m), (long long)b);
+            const float2 b = lba[8 * m];
+            if (b.x > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowa + t + 8 * m),
+                          (long long)pack_best(__float_as_uint(b.x), __float_as_uint(b.y)));
         }
         if ((mb >> m) & 1u) {
-            const int64_t b = lbb[8 * m];
-            if (b > kBestInit) atomicMax(reinterpret_cast<long long *>(best + rowb + t + 8 * m), (long long)b);
+            const float2 b = lbb[8 * m];
+            if (b.x > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowb + t + 8 * m),
+                          (long long)pack_best(__float_as_uint(b.x), __float_as_uint(b.y)));
         }
     }
 }
