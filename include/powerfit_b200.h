@@ -124,6 +124,20 @@ int pfb_search_host(pfb_plan *plan, const float *target, const uint8_t *lcc_mask
                     const float *tmpl, const float *mask, float norm_factor, int mask_is_binary,
                     const double *rotmats, int R, int rot_index_offset, float *lcc, int32_t *rot);
 
+/* ---- solution extraction: device half of Analyzer._watershed ---- */
+
+/* numpy `corr.max()` of analyzer.py:84 on a float32 device grid of n values (current device):
+ * writes the maximum (NaN if any value is NaN, like numpy) to *max_out (device).  scratch = one
+ * device int32. */
+int pfb_lcc_max(const float *lcc, int64_t n, float *max_out, int32_t *scratch, void *stream);
+
+/* The voxels that can belong to any labelled feature of analyzer.py:90-93: stream compaction of
+ * {i : lcc[i] >= cutoff} into idx/val (device, capacity cap, arbitrary order).  *count (device)
+ * receives the number found, which may exceed cap -- the caller then retries with a larger
+ * buffer. */
+int pfb_peak_candidates(const float *lcc, int64_t n, float cutoff, int32_t cap, int32_t *idx, float *val,
+                        int32_t *count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,8 @@ What is restated, with the reference lines it follows (paths below
 ``OracleCorrelator``       ``powerfitter.py:166-393`` (BaseCorrelator + CPUCorrelator)
 ``partition_rotations``    ``powerfitter.py:95-108``
 ``combine_partials``       ``powerfitter.py:146-163``
+``watershed_positions``    ``analyzer.py:80-95`` (next row N1; pinned by
+``solution_rows``          ``analyzer.py:58-78``  tests/golden/analyzer_solutions.npz)
 =========================  ======================================================
 
 The FFT arithmetic itself is third-party in the reference (pyFFTW>=0.12 wrapping
@@ -326,3 +328,34 @@ def parallel_scan(target, template, mask, rotations, laplace=False, nproc=1):
         with mp.get_context("fork").Pool(nproc) as pool:
             parts = pool.map(_scan_block, jobs)
     return combine_partials(parts, rotations.shape[0] // nproc, np.asarray(target).shape)
+
+
+# --------------------------------------------------------------------------- #
+# Solution extraction -- dense restatement of the reference Analyzer
+def watershed_positions(corr, steps=5):
+    """``analyzer.py:80-95``: for ``steps`` cutoffs from the maximum down to half of it, label
+    ``corr >= cutoff`` (scipy default 6-connectivity) and collect the position of the maximum
+    of every feature."""
+    from scipy.ndimage import label, maximum_position
+    top = corr.max()
+    low = 0.5 * top
+    delta = (top - low) / steps
+    level = top
+    found = set()
+    for _ in range(steps):
+        level = level - delta
+        lab, count = label(corr >= level)
+        found.update(tuple(int(c) for c in p) for p in maximum_position(corr, lab, list(range(1, count + 1))))
+    return found
+
+
+def solution_rows(corr, rotmat, rotmat_ind, positions, voxelspacing=1, origin=(0, 0, 0), z_sigma=1):
+    """``analyzer.py:58-78``: [cc, Fisher z, relative z, x, y, z, a11..a33] per position,
+    sorted by cc descending."""
+    rows = []
+    for pos in positions:
+        cc = corr[pos]
+        fz = 0.5 * (np.log(1 + cc) - np.log(1 - cc))
+        zyx = [c * voxelspacing + o for c, o in zip(pos, origin[::-1])]
+        rows.append([cc, fz, fz / z_sigma, zyx[2], zyx[1], zyx[0]] + list(np.ravel(rotmat[int(rotmat_ind[pos])])))
+    return sorted(rows, key=lambda r: r[0], reverse=True)

@@ -317,3 +317,42 @@ def test_fused_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace):
         assert np.abs(lcc - g_lcc)[~same].max(initial=0) < 2e-5
     assert np.array_equal(results["fused"][0], results["fused_noprune"][0])
     assert np.array_equal(results["fused"][1], results["fused_noprune"][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["scan_config1_64", "scan_32_plain", "scan_24_laplace_cw",
+                                  "scan_config2_128_subset", "rough"])
+def test_analyzer_matches_reference_solutions(pfb, name, tmp_path):
+    """N1: device max + compaction, host labelling -> the reference Analyzer's positions, rows and
+    solutions.out text (golden generated by the real reference, tests/golden/make_golden_analyzer.py)."""
+    from test_oracle import analyzer_case
+    from powerfit_b200.analyzer import Analyzer
+    lcc, rot, rotations, steps, vs, origin, zs, positions, solutions, text = analyzer_case(name)
+    a = Analyzer(lcc, rotations, rot, steps=steps, voxelspacing=vs, origin=origin, z_sigma=zs)
+    assert a._positions == positions
+    rows = np.array(a.solutions, dtype=np.float64)
+    assert rows.shape == solutions.shape and np.array_equal(rows[:, 0], solutions[:, 0])
+    assert np.allclose(rows, solutions, rtol=0, atol=1e-12)
+    out = tmp_path / "solutions.out"
+    a.tofile(str(out))
+    assert out.read_text() == text
+    assert 0 < a.last_candidates < 0.2 * lcc.size
+
+
+@pytest.mark.gpu
+def test_analyzer_on_device_tensor_and_search_result(pfb, oracle):
+    """Whole hand-off: search on the GPU, analyse the device-resident LCC grid, compare the
+    solutions with the CPU restatement run on the same grids."""
+    import torch
+    from powerfit_b200 import synth
+    from powerfit_b200.analyzer import Analyzer
+    case = synth.make_case(n=32, voxelspacing=2.0, resolution=8.0, n_res=80, rg=8.0, n_copies=2, seed=9)
+    rots = synth.random_rotations(40, seed=2)
+    c = run_scan(pfb, case.target, case.template, case.mask, rots, False, batch=8)
+    dev = torch.from_numpy(c.lcc).cuda()
+    a = Analyzer(dev, rots, c.rot, voxelspacing=2.0, origin=(1.0, 2.0, 3.0), z_sigma=0.05)
+    pos = oracle.watershed_positions(c.lcc, 5)
+    assert a._positions == pos
+    want = np.array(oracle.solution_rows(c.lcc, rots, c.rot, pos, 2.0, (1.0, 2.0, 3.0), 0.05), dtype=np.float64)
+    got = np.array(a.solutions, dtype=np.float64)
+    assert np.allclose(got, want, rtol=0, atol=1e-12)

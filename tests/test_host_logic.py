@@ -119,3 +119,23 @@ def test_world_size_2_gloo_merge(tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
     codes = [p.wait(timeout=300) for p in procs]
     assert codes == [0, 0]
+
+
+@pytest.mark.parametrize("name", ["scan_config1_64", "scan_32_plain", "scan_24_laplace_cw",
+                                  "scan_config2_128_subset", "rough"])
+def test_sparse_feature_maxima_equals_reference_labelling(name):
+    """Host half of the Analyzer (N1): connected components on the short above-cutoff list give
+    the positions scipy label + maximum_position give on the full grid (reference golden).  The
+    device compaction is replaced by numpy here; the GPU test runs the real kernels."""
+    from test_oracle import analyzer_case
+    from powerfit_b200.analyzer import sparse_feature_maxima, watershed_cutoffs
+    lcc, rot, rotations, steps, vs, origin, zs, positions, solutions, _ = analyzer_case(name)
+    cut = watershed_cutoffs(lcc.max(), steps)
+    assert all(c.dtype == lcc.dtype for c in cut)
+    idx = np.nonzero(lcc.ravel() >= cut[-1])[0]
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(idx.size)                       # the device returns them in any order
+    lin = sparse_feature_maxima(idx[perm], lcc.ravel()[idx][perm], lcc.shape, cut)
+    got = set(tuple(int(c) for c in np.unravel_index(i, lcc.shape)) for i in lin)
+    assert got == positions
+    assert idx.size < 0.2 * lcc.size

@@ -164,3 +164,32 @@ def test_partition_matches_reference_rule(oracle):
     assert oracle.partition_rotations(10, 3) == [(0, 3), (3, 6), (6, 10)]
     assert oracle.partition_rotations(648, 8)[-1] == (567, 648)
     assert oracle.partition_rotations(5, 1) == [(0, 5)]
+
+
+ANALYZER_CASES = ["scan_config1_64", "scan_32_plain", "scan_24_laplace_cw", "scan_config2_128_subset", "rough"]
+
+
+def analyzer_case(name):
+    """(lcc, rot, rotations, steps, voxelspacing, origin, z_sigma, positions, solutions, text)."""
+    g = load_golden("analyzer_solutions")
+    if name == "rough":
+        lcc, rot, rotations = g["rough_lcc"], g["rough_rot"], g["rough_rotations"]
+    else:
+        s = load_golden(name)
+        lcc, rot, rotations = s["lcc"], s["rot"], s["rotations"]
+    prm = g[name + "_params"]
+    return (lcc, rot, rotations, int(prm[0]), float(prm[1]), tuple(float(v) for v in prm[2:5]), float(prm[5]),
+            set(tuple(int(c) for c in p) for p in g[name + "_positions"]), g[name + "_solutions"],
+            str(g[name + "_text"]))
+
+
+@pytest.mark.parametrize("name", ANALYZER_CASES)
+def test_oracle_watershed_matches_reference_analyzer(oracle, name):
+    """N1 oracle pin: feature maxima and solution rows equal the real reference Analyzer's."""
+    lcc, rot, rotations, steps, vs, origin, zs, positions, solutions, _ = analyzer_case(name)
+    pos = oracle.watershed_positions(lcc, steps)
+    assert pos == positions
+    rows = np.array(oracle.solution_rows(lcc, rotations, rot, pos, vs, origin, zs), dtype=np.float64)
+    assert rows.shape == solutions.shape
+    assert np.array_equal(rows[:, 0], solutions[:, 0])                 # same order, same cc
+    assert np.allclose(rows, solutions, rtol=0, atol=1e-12)
