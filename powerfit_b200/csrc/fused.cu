@@ -247,6 +247,22 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
         __syncthreads();
         if (q >= nplanes) break;
 
+        // pull the support rows of the CTA's next plane towards L2 while phase 2 runs (one 128-byte line
+        // per thread): the row loop's direct loads then see L2 instead of HBM latency
+        {
+            const int qn = q + gridDim.x;
+            const int nlines = nzv * 2 * __popc(ymask);
+            if (qn < nplanes && (int)threadIdx.x < nlines) {
+                const int pair = qn % npairs, vol = (qn / npairs) % 3, kx = qn / (3 * npairs);
+                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+                const int j = threadIdx.x / (2 * __popc(ymask)), l = threadIdx.x % (2 * __popc(ymask));
+                const int z = (j - rs + N) % N, tile = __fns(ymask, 0, (l >> 1) + 1);
+                const float4 *a = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H + (size_t)z * slab +
+                                  16 * tile + 8 * (l & 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+
         // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs ky, ky+H)
         {
             const int vol = (q / npairs) % 3, kx = q / (3 * npairs);
