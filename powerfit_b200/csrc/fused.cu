@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 namespace pfb {
 
@@ -350,47 +351,54 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
         __syncthreads();
         float4 *tile = tile0 + (item % NBUF) * N * TP;
         const int p = p0 + item / 3, vi = item % 3;
-        {
-            C2 v[E];
-#pragma unroll
-            for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + (t + 8 * n1) * TP + rp);
-            pencil2_stage1<8, E>(v, tile + rp, TP, t, tw);
-        }
         const uint32_t ia = (uint32_t)(first_index + 2 * p);
         const bool have_b = 2 * p + 1 < count;
+        // one straight-line body per volume kind (VI = 0 ave2, 1 ave, 2 gcc)
+        auto run_item = [&](auto vi_tag) {
+            constexpr int VI = decltype(vi_tag)::value;
+            {
+                C2 v[E];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            // outputs x = t + 8 m, m = q + Q k0, of this chunk go straight into the epilogue
-            C2 a[8];
-            pencil2_stage2<8>(a, tile + rp, TP, t, q);
-            if (q == Q - 1 && NBUF == 1) {
-                __syncthreads();       // every pencil is out of the tile: refill it while the arithmetic runs
-                if (item + 1 < nitems) prefetch(item + 1);
+                for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + (t + 8 * n1) * TP + rp);
+                pencil2_stage1<8, E>(v, tile + rp, TP, t, tw);
             }
 #pragma unroll
-            for (int k0 = 0; k0 < 8; ++k0) {
-                const int m = q + Q * k0;
-                if (vi == 0) {
-                    sd[m] = a[k0];                                     // ave2
-                } else if (vi == 1) {                                  // 1/sqrt(N ave2 - ave^2)
-                    // var <= 0 gives inf / NaN exactly where the reference's gcc/sqrt(var) does
-                    const float2 vr = psub(pmul(sd[m].re, pdup(norm)), pmul(a[k0].re, a[k0].re));
-                    const float2 vq = psub(pmul(sd[m].im, pdup(norm)), pmul(a[k0].im, a[k0].im));
-                    sd[m].re = make_float2(rsqrtf(vr.x), rsqrtf(vr.y));
-                    sd[m].im = make_float2(rsqrtf(vq.x), rsqrtf(vq.y));
-                } else {
-                    // (row a, row b) of rotation a / rotation b
-                    const float2 la = pmul(a[k0].re, sd[m].re), lb = pmul(a[k0].im, sd[m].im);
-                    // best of the pair first (ties and NaN: rotation a, the lower index, stays)
-                    const bool sa = have_b && (lb.x > la.x || !(la.x == la.x));
-                    const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
-                    const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
-                    const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
-                    if (((ma >> m) & 1u) && ca > lba[8 * m].x) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
-                    if (((mb >> m) & 1u) && cb > lbb[8 * m].x) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
+            for (int q = 0; q < Q; ++q) {
+                // outputs x = t + 8 m, m = q + Q k0, of this chunk go straight into the epilogue
+                C2 a[8];
+                pencil2_stage2<8>(a, tile + rp, TP, t, q);
+                if (q == Q - 1 && NBUF == 1) {
+                    __syncthreads();       // every pencil is out of the tile: refill it while the arithmetic runs
+                    if (item + 1 < nitems) prefetch(item + 1);
+                }
+#pragma unroll
+                for (int k0 = 0; k0 < 8; ++k0) {
+                    const int m = q + Q * k0;
+                    if (VI == 0) {
+                        sd[m] = a[k0];                                     // ave2
+                    } else if (VI == 1) {                                  // 1/sqrt(N ave2 - ave^2)
+                        // var <= 0 gives inf / NaN exactly where the reference's gcc/sqrt(var) does
+                        const float2 vr = psub(pmul(sd[m].re, pdup(norm)), pmul(a[k0].re, a[k0].re));
+                        const float2 vq = psub(pmul(sd[m].im, pdup(norm)), pmul(a[k0].im, a[k0].im));
+                        sd[m].re = make_float2(rsqrtf(vr.x), rsqrtf(vr.y));
+                        sd[m].im = make_float2(rsqrtf(vq.x), rsqrtf(vq.y));
+                    } else {
+                        // (row a, row b) of rotation a / rotation b
+                        const float2 la = pmul(a[k0].re, sd[m].re), lb = pmul(a[k0].im, sd[m].im);
+                        // best of the pair first (ties and NaN: rotation a, the lower index, stays)
+                        const bool sa = have_b && (lb.x > la.x || !(la.x == la.x));
+                        const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
+                        const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
+                        const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
+                        if (((ma >> m) & 1u) && ca > lba[8 * m].x) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
+                        if (((mb >> m) & 1u) && cb > lbb[8 * m].x) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
+                    }
                 }
             }
-        }
+        };
+        if (vi == 0) run_item(std::integral_constant<int, 0>{});
+        else if (vi == 1) run_item(std::integral_constant<int, 1>{});
+        else run_item(std::integral_constant<int, 2>{});
         if (NBUF == 2) __syncthreads();   // this item's tile may be refilled by the next iteration's prefetch
     }
 #pragma unroll
