@@ -55,7 +55,8 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
 int pfb_plan_destroy(pfb_plan *plan);
 
 /* Query: 0 nz, 1 ny, 2 nx, 3 rmax, 4 batch, 5 device, 6 fused-path-available,
- * 7 kernel launches since plan creation (low 31 bits). */
+ * 7 kernel launches since plan creation (low 31 bits), 8 support radius of the template in
+ * voxels (fused path), 9 class-decimated fused kernels in use (256^3; 128^3 with PFB_CLS=1). */
 int pfb_plan_info(const pfb_plan *plan, int what, int64_t *value);
 
 /* GPUCorrelator.__init__ (powerfitter.py:410-420): takes the normalised (and, if the

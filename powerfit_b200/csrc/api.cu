@@ -120,10 +120,10 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     DeviceGuard guard(device);
     if (!guard.ok) { delete h; set_error("cudaSetDevice failed"); return PFB_ERR_CUDA; }
     if (max_batch <= 0) {
-        // default: as many rotations in flight as fit ~4 GB of work buffers, 2..64 (measured at 128^3:
+        // default: as many rotations in flight as fit ~16 GB of work buffers, 2..64 (measured at 128^3:
         // 32 -> 41.0k, 48 -> 41.8k, 64 -> 42.3k rotations/s; longer launches amortise tails and prologues)
         const long per_pair = 6L * p->V * (long)sizeof(float2);
-        long pairs = (4096L << 20) / per_pair;
+        long pairs = (16384L << 20) / per_pair;
         pairs = std::max(1L, std::min(32L, pairs));
         max_batch = (int)(2 * pairs);
     }
@@ -155,9 +155,11 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     p->fused = fused_supported(nz, ny, nx);
     if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;
     if (p->fused) {
+        p->cls = nx == 256;
+        if (const char *e = getenv("PFB_CLS")) p->cls = p->cls || (nx == 128 && atoi(e) != 0);
         PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
-        PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 8);
+        PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 16);
         PFB_ALLOC(p->tmplq, sizeof(float4) * p->V);
         if (const char *e = getenv("PFB_OVERLAP")) p->overlap = atoi(e) != 0;
         if (const char *e = getenv("PFB_B_THREADS")) p->b_threads = atoi(e) == 256 ? 256 : 512;
@@ -182,7 +184,8 @@ int pfb_plan_destroy(pfb_plan *h) {
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->B2, p->tmplq};
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->B2, p->tmplq,
+                    p->cls_twN, p->cls_twM, p->cls_twh, p->cls_fold};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (int i = 0; i < 2; ++i) {
@@ -206,6 +209,7 @@ int pfb_plan_info(const pfb_plan *h, int what, int64_t *value) {
         case 5: *value = p->device; break;
         case 6: *value = p->fused ? 1 : 0; break;
         case 8: *value = p->rs; break;
+        case 9: *value = p->cls ? 1 : 0; break;
         case 7: *value = (int64_t)(p->launches & 0x7FFFFFFF); break;
         default: set_error("pfb_plan_info: unknown field"); return PFB_ERR_INVALID;
     }

@@ -87,6 +87,13 @@ int fused_prepare_template(Plan *p, cudaStream_t s);
 int fused_batch(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s);
 int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s);
 int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
+int launch_fused_a(Plan *p, int first, int count, cudaStream_t s);
+
+// class-decimated fused path (fused_cls.cu): N = 256, optionally N = 128
+int cls_init(Plan *p);
+int cls_prepare_target(Plan *p, cudaStream_t s);
+int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s);
+int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
 
 struct Plan {
     int nz = 0, ny = 0, nx = 0, rmax = 0, device = 0;
@@ -108,6 +115,10 @@ struct Plan {
     uint32_t *mbits = nullptr;                     // lcc_mask bit-packed in kernel C's lane layout
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;
+    // class-decimated variant of kernels B and C (fused_cls.cu)
+    bool cls = false;
+    float2 *cls_twN = nullptr, *cls_twM = nullptr, *cls_twh = nullptr;
+    float4 *cls_fold = nullptr;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]
     float2 *B = nullptr;                           // product / inverse work: [batch/2][3][V]
     // fused path, overlapped mode: kernel C of batch n runs on a second stream next to kernels A and

@@ -90,6 +90,13 @@ __device__ __forceinline__ void stg_c2(float4 *p, C2 v) {
 }
 __device__ __forceinline__ C2 c2_zero() { C2 r; r.re = make_float2(0.f, 0.f); r.im = make_float2(0.f, 0.f); return r; }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
+
 // ------------------------------------------------------------------ complex algebra, both types
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -192,34 +199,35 @@ template <class T> struct DftReg<4, T> { static __device__ __forceinline__ void 
 template <class T> struct DftReg<8, T> { static __device__ __forceinline__ void run(T (&v)[8]) { dft8(v); } };
 template <class T> struct DftReg<16, T> { static __device__ __forceinline__ void run(T (&v)[16]) { dft16(v); } };
 
-// ------------------------------------------------------------------ scalar pencil (8 lanes x E)
-// in : v[n1] = x[t + 8 n1]       out: v[m] = X[t + 8 m]
-// scratch[p * stride], p < 8E, is the pencil's shared-memory storage (clobbered).
-template <int E>
+// ------------------------------------------------------------------ scalar pencil (L lanes x E)
+// in : v[n1] = x[t + L n1]       out: v[m] = X[t + L m]
+// scratch[p * stride], p < L*E, is the pencil's shared-memory storage (clobbered).
+template <int E, int L = 8>
 __device__ __forceinline__ void fft_pencil(float2 (&v)[E], float2 *scratch, int stride, int t,
                                            const float2 (&tw)[E], bool active) {
+    static_assert(E % L == 0, "E must be a multiple of L");
     DftReg<E, float2>::run(v);
 #pragma unroll
     for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulf(v[k1], tw[k1]);
     __syncwarp();
     if (active) {
 #pragma unroll
-        for (int k1 = 0; k1 < E; ++k1) scratch[(k1 * 8 + (t ^ (k1 & 7))) * stride] = v[k1];
+        for (int k1 = 0; k1 < E; ++k1) scratch[(k1 * L + (t ^ (k1 & (L - 1)))) * stride] = v[k1];
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < E / 8; ++q) {
-        float2 a[8];
+    for (int q = 0; q < E / L; ++q) {
+        float2 a[L];
         if (active) {
 #pragma unroll
-            for (int n0 = 0; n0 < 8; ++n0) a[n0] = scratch[((t + 8 * q) * 8 + (n0 ^ t)) * stride];
+            for (int n0 = 0; n0 < L; ++n0) a[n0] = scratch[((t + L * q) * L + (n0 ^ t)) * stride];
         } else {
 #pragma unroll
-            for (int n0 = 0; n0 < 8; ++n0) a[n0] = make_float2(0.f, 0.f);
+            for (int n0 = 0; n0 < L; ++n0) a[n0] = make_float2(0.f, 0.f);
         }
-        dft8(a);
+        DftReg<L, float2>::run(a);
 #pragma unroll
-        for (int k0 = 0; k0 < 8; ++k0) v[(E / 8) * k0 + q] = a[k0];
+        for (int k0 = 0; k0 < L; ++k0) v[(E / L) * k0 + q] = a[k0];
     }
     __syncwarp();
 }
@@ -227,7 +235,7 @@ __device__ __forceinline__ void fft_pencil(float2 (&v)[E], float2 *scratch, int 
 template <int E>
 __device__ __forceinline__ void load_twiddles(float2 (&tw)[E], const float2 *__restrict__ twN, int t) {
 #pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) tw[k1] = __ldg(twN + t * k1);      // t*k1 < 8E = N
+    for (int k1 = 0; k1 < E; ++k1) tw[k1] = __ldg(twN + t * k1);      // t*k1 < L*E = N
 }
 
 // ------------------------------------------------------------------ packed pencil (LANES x E), two numbers per element
@@ -319,6 +327,30 @@ __device__ __forceinline__ void fft_pencil2_mul(C2 (&v)[E], float4 *scratch, int
 #pragma unroll
             for (int k0 = 0; k0 < LANES; ++k0) f0[k0] = fn[k0];
         }
+    }
+    __syncwarp();
+}
+
+// Same, for wide pencils (LANES = 16) where holding every factor across the transform would
+// spill: the factors are fetched in two halves around stage 2.
+template <int LANES, int E, class TW>
+__device__ __forceinline__ void fft_pencil2_mul_late(C2 (&v)[E], float4 *scratch, int stride, int t, const TW &tw,
+                                                     const float4 *__restrict__ f) {
+    constexpr int Q = E / LANES, HL = LANES / 2;
+    pencil2_stage1<LANES, E>(v, scratch, stride, t, tw);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        C2 fa[HL];
+#pragma unroll
+        for (int k0 = 0; k0 < HL; ++k0) fa[k0] = ldg_c2(f + LANES * (Q * k0 + q));
+        C2 a[LANES];
+        pencil2_stage2<LANES>(a, scratch, stride, t, q);
+#pragma unroll
+        for (int k0 = 0; k0 < HL; ++k0) v[Q * k0 + q] = cmul(a[k0], fa[k0]);
+#pragma unroll
+        for (int k0 = 0; k0 < HL; ++k0) fa[k0] = ldg_c2(f + LANES * (Q * (k0 + HL) + q));
+#pragma unroll
+        for (int k0 = 0; k0 < HL; ++k0) v[Q * (k0 + HL) + q] = cmul(a[k0 + HL], fa[k0]);
     }
     __syncwarp();
 }

@@ -35,13 +35,14 @@
 namespace pfb {
 
 // ------------------------------------------------------------------------------- kernel A
-template <int N>
-__global__ void __launch_bounds__(256)
+// L lanes per x pencil (E = N / L points each); 32 rows per CTA -> 32 L threads
+template <int N, int L>
+__global__ void __launch_bounds__(32 * L)
 fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ mask,
                          const double *__restrict__ rot, int first, int count, int nsig,
                          float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
                          unsigned ymask, int nzv) {
-    constexpr int E = N / 8, TP = 33;
+    constexpr int E = N / L, TP = 33, THREADS = 32 * L;
     extern __shared__ float2 smem[];
     float2 *tile_t = smem, *tile_m = smem + N * TP;
     const int pair = blockIdx.y;
@@ -61,14 +62,14 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
     // ---- gather the 32 x N tile of both signals (zeros outside the sphere / support)
     //      zero-fill first, then visit only the x offsets inside the support box [xlo, rs];
     //      offset -N/2 is skipped: it aliases index N/2, which belongs to offset +N/2.
-    for (int idx = threadIdx.x; idx < N * TP; idx += 256) {
+    for (int idx = threadIdx.x; idx < N * TP; idx += THREADS) {
         tile_t[idx] = make_float2(0.f, 0.f);
         tile_m[idx] = make_float2(0.f, 0.f);
     }
     __syncthreads();
     const int xlo = max(-rs, -(N / 2 - 1)), W = rs - xlo + 1;
     const int lim2 = min(rs2, (N / 2) * (N / 2));
-    for (int idx = threadIdx.x; idx < 32 * W; idx += 256) {
+    for (int idx = threadIdx.x; idx < 32 * W; idx += THREADS) {
         const int r = idx / W, ox = idx % W + xlo;
         const int iy = y0 + r;
         const int oy = iy <= N / 2 ? iy : iy - N;
@@ -91,23 +92,23 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
 
     // ---- x transforms: thread (row r, t)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = lane & 7, r = warp + 8 * (lane >> 3);
+    const int t = lane & (L - 1), r = warp + L * (lane / L);
     float2 tw[E];
     load_twiddles<E>(tw, twN, t);
     float2 v[E], v2[E];
 #pragma unroll
-    for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + 8 * n1) * TP + r];
-    fft_pencil<E>(v, tile_t + r, TP, t, tw, true);
+    for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + r];
+    fft_pencil<E, L>(v, tile_t + r, TP, t, tw, true);
 #pragma unroll
-    for (int m = 0; m < E; ++m) tile_t[(t + 8 * m) * TP + r] = v[m];
+    for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + r] = v[m];
 #pragma unroll
     for (int n1 = 0; n1 < E; ++n1) {
-        v[n1] = tile_m[(t + 8 * n1) * TP + r];
+        v[n1] = tile_m[(t + L * n1) * TP + r];
         v2[n1] = make_float2(v[n1].x * v[n1].x, v[n1].y * v[n1].y);
     }
-    fft_pencil<E>(v, tile_m + r, TP, t, tw, true);
+    fft_pencil<E, L>(v, tile_m + r, TP, t, tw, true);
 #pragma unroll
-    for (int m = 0; m < E; ++m) tile_m[(t + 8 * m) * TP + r] = v[m];
+    for (int m = 0; m < E; ++m) tile_m[(t + L * m) * TP + r] = v[m];
     __syncthreads();
 
     // ---- coalesced write-out: 32 consecutive y (256 B) per kx, pairs of y interleaved
@@ -117,7 +118,7 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
     float4 *X14 = reinterpret_cast<float4 *>(X1);
     float4 *o_t = X14 + ((size_t)(pair * nsig + 0) * N + z) * slab + y0 / 2;      // X1[pair][sig][z][kx][y/2]
     float4 *o_m = X14 + ((size_t)(pair * nsig + 1) * N + z) * slab + y0 / 2;
-    for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
+    for (int idx = threadIdx.x; idx < 16 * N; idx += THREADS) {
         const int kx = idx >> 4, jj = idx & 15;
         const float2 a = tile_t[kx * TP + 2 * jj], b = tile_t[kx * TP + 2 * jj + 1];
         o_t[(size_t)kx * H + jj] = make_float4(a.x, b.x, a.y, b.y);
@@ -126,12 +127,12 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
     }
     if (nsig == 3) {
         __syncthreads();
-        fft_pencil<E>(v2, tile_t + r, TP, t, tw, true);
+        fft_pencil<E, L>(v2, tile_t + r, TP, t, tw, true);
 #pragma unroll
-        for (int m = 0; m < E; ++m) tile_t[(t + 8 * m) * TP + r] = v2[m];
+        for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + r] = v2[m];
         __syncthreads();
         float4 *o_2 = X14 + ((size_t)(pair * nsig + 2) * N + z) * slab + y0 / 2;
-        for (int idx = threadIdx.x; idx < 16 * N; idx += 256) {
+        for (int idx = threadIdx.x; idx < 16 * N; idx += THREADS) {
             const int kx = idx >> 4, jj = idx & 15;
             const float2 a = tile_t[kx * TP + 2 * jj], b = tile_t[kx * TP + 2 * jj + 1];
             o_2[(size_t)kx * H + jj] = make_float4(a.x, b.x, a.y, b.y);
@@ -147,13 +148,6 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
 //   phase 2  columns ky and ky+N/2 as two independent pencils: forward z, multiply with the
 //            map spectrum (stored in the same pairing, Fpk[kx][ky][kz]), inverse z
 //   phase 3  rows, inverse y : split-in -> adjacent-out, straight to X2
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
-
 template <int N> struct FusedCfg;
 template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8; };
 template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8; };
@@ -503,8 +497,9 @@ template <int N> static int fused_init_n(Plan *p) {
     if ((rc = upload_pencil_twiddles(Cfg::LN, Cfg::EN, &p->twdN))) return rc;
     if ((rc = upload_pencil_twiddles(Cfg::LM, Cfg::EM, &p->twdM))) return rc;
     constexpr int TP = 33;
-    PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
+    if (p->cls) return cls_init(p);
     PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_b<N>()));
     if (N >= 128)
@@ -517,14 +512,18 @@ template <int N> static int fused_init_n(Plan *p) {
     return PFB_OK;
 }
 
-bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (nx == 64 || nx == 128); }
+bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (nx == 64 || nx == 128 || nx == 256); }
 
 int fused_init(Plan *p) {
     if (p->nx == 64) return fused_init_n<64>(p);
-    return fused_init_n<128>(p);
+    if (p->nx == 128) return fused_init_n<128>(p);
+    PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * 256 * 33 * sizeof(float2))));
+    return cls_init(p);
 }
 
 int fused_prepare_target(Plan *p, cudaStream_t s) {
+    if (p->cls) return cls_prepare_target(p, s);
     const int N = p->nx;
     dim3 grid(N / 32, N / 32, N / 2), block(32, 8);
     { LaunchScope ls(p, KC_OTHER, s);
@@ -569,18 +568,31 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
     return PFB_OK;
 }
 
-// front half of a batch: A (rotate + x) and B (y, z, multiply, z, y) into the work buffer X2
-template <int N, int BT>
-static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
+// kernel A of a batch: rotate + forward x into the work buffer X1
+template <int N, int L>
+static int fused_a_n(Plan *p, int first, int count, cudaStream_t s) {
     constexpr int TP = 33;
     const int npairs = (count + 1) / 2;
     const int nzv = std::min(2 * p->rs + 1, N);
     const int nyt = __builtin_popcount(p->ymask);
-    {
-        LaunchScope ls(p, KC_FUSED_A, s);
-        fused_rotate_fftx_kernel<N><<<dim3(nzv * nyt, npairs), 256, 2 * N * TP * sizeof(float2), s>>>(
-            p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->ymask, nzv);
-    }
+    LaunchScope ls(p, KC_FUSED_A, s);
+    fused_rotate_fftx_kernel<N, L><<<dim3(nzv * nyt, npairs), 32 * L, 2 * N * TP * sizeof(float2), s>>>(
+        p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->ymask, nzv);
+    return PFB_OK;
+}
+
+int launch_fused_a(Plan *p, int first, int count, cudaStream_t s) {
+    if (p->nx == 64) return fused_a_n<64, 8>(p, first, count, s);
+    if (p->nx == 128) return fused_a_n<128, 8>(p, first, count, s);
+    return fused_a_n<256, 16>(p, first, count, s);
+}
+
+// front half of a batch: A (rotate + x) and B (y, z, multiply, z, y) into the work buffer X2
+template <int N, int BT>
+static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
+    const int npairs = (count + 1) / 2;
+    int rc = launch_fused_a(p, first, count, s);
+    if (rc) return rc;
     {
         LaunchScope ls(p, KC_FUSED_B, s);
         const int nplanes = N * 3 * npairs;
@@ -618,12 +630,14 @@ static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int
 }
 
 int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
+    if (p->cls) return cls_front(p, first, count, X2, s);
     if (p->nx == 64) return fused_front_n<64, 256>(p, first, count, X2, s);
     if (p->b_threads == 256) return fused_front_n<128, 256>(p, first, count, X2, s);
     return fused_front_n<128, 512>(p, first, count, X2, s);
 }
 
 int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
+    if (p->cls) return cls_back(p, first, count, rot_index_offset, best, X2, s);
     if (p->nx == 64) return fused_back_n<64>(p, first, count, rot_index_offset, best, X2, s);
     return fused_back_n<128>(p, first, count, rot_index_offset, best, X2, s);
 }

@@ -1,0 +1,468 @@
+// Class-decimated fused pipeline for cubic grids whose (y,z) plane does not fit one SM's shared
+// memory (N = 256; selectable for N = 128).  Same three kernels as fused.cu,
+//
+//   A  fused_rotate_fftx   (fused.cu)  rotate + forward x            -> X1[pair][sig][z][kx][y]
+//   B  cls_fftyz_mul                   forward y,z * FT(map), inverse z,y of ONE ky class
+//   C  cls_ifftx_lcc                   class combine, inverse x, LCC, running best
+//
+// but kernel B works on a quarter (N = 256) or half (N = 128) of a (y,z) plane:
+// with NB = N/64 and ky = NB k' + b the first radix-NB step of a decimation-in-frequency
+// y transform splits the outputs into NB residue classes b, each a 64-point transform of the
+// folded row   g_b[n] = W_N^(n b) sum_j x[n + 64 j] W_NB^(j b),   n < 64.
+// The z transforms, the multiplication with the map spectrum and the inverse z transforms act
+// on every ky column on its own, so a CTA that owns class b of plane kx needs only the
+// N x 64 tile of its class (132 KB at N = 256) -- at the price of reading the (support-pruned,
+// L2-resident) input rows NB times.  The inverse y transform of class b yields
+//   G_b[n'] = sum_k' X[NB k' + b] W_64^(n' k'),   y[n' + 64 j] = sum_b W_NB^(j b) W_N^(n' b) G_b[n'],
+// and that last radix-NB butterfly is linear and acts per (z, kx), so it commutes with the
+// inverse x transform: kernel B stores G_b, and kernel C applies the butterfly to its tile in
+// shared memory before the x pencils run.  HBM traffic stays at the three-kernel minimum
+// (n_f S pruned + 3 S + 3 S per rotation); nothing is written that the 128^3 pipeline would
+// not write.  (K numbers / reference lines: see fused.cu.)
+#include "common.cuh"
+#include "fft_core.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
+
+namespace pfb {
+
+template <int N> struct ClsCfg;
+// LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
+// class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows)
+template <> struct ClsCfg<128> { static constexpr int LN = 8, EN = 16, THREADS = 256, CTAS = 2, NB = 2, PPT = 8, LC = 8; };
+template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16; };
+
+// ------------------------------------------------------------------------------- kernel B
+// Plane q = ((kx * 3 + volume) * npairs + pair) * NB + b; the grid is a multiple of NB, so a
+// persistent CTA keeps its class b = blockIdx.x % NB for all its planes and neighbouring CTAs
+// share the input rows (b fastest) and the map-spectrum tile (pair next).
+// Tile layout: plane[z][c], c < 32, float4 = columns (k' = c, c + 32) in split form.
+template <int N>
+__global__ void __launch_bounds__(ClsCfg<N>::THREADS, ClsCfg<N>::CTAS)
+cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fc,
+                     const float4 *__restrict__ F2c, const float2 *__restrict__ twN_g,
+                     const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g,
+                     const float4 *__restrict__ fold_g, int rs, unsigned ymask, int nsig, int nplanes) {
+    using Cfg = ClsCfg<N>;
+    constexpr int H = N / 2, HC = 32, P = 33, NB = Cfg::NB, PPT = Cfg::PPT;
+    constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
+    constexpr int LM = 4, EM = 8, GM = 8;                        // row pencils: packed 32 points (64-point rows)
+    constexpr int THREADS = Cfg::THREADS, NW = THREADS / 32;
+    extern __shared__ float4 smem4[];
+    float4 *plane = smem4;                                        // [N][P]
+    float4 *dummy = plane + N * P;                                // [GM][P] scratch rows of idle lanes
+    float4 *fold_s = dummy + GM * P;                              // [32] W_N^(n b), n = 2 idx, 2 idx + 1
+    float2 *twN = reinterpret_cast<float2 *>(fold_s + 32);        // [EN][LN] W_N^(t k1)
+    float2 *twM = twN + N;                                        // [EM][LM] W_32^(t k1)
+    float2 *twh_s = twM + 32;                                     // [32] W_64^k of the split radix-2 step
+    const size_t slab = (size_t)N * H;                            // float4 per z of X1 / X2
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // row pencils: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo
+    // the 128-byte bank window (P = 33): conflict-free 16-byte accesses
+    const int tM = lane & 3, gM = (lane >> 3) + 4 * ((lane >> 2) & 1);
+    const int tN = lane & (LN - 1), gN = lane / LN;
+    const int nzv = min(2 * rs + 1, N);
+    const int npairs = nplanes / (3 * N * NB);
+    const int b = blockIdx.x % NB;
+
+    int q = blockIdx.x;          // plane whose phase 1 comes next
+    int qcur = -1;               // plane whose phase 2 is done (phase 3 pending)
+    for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
+    for (int i = threadIdx.x; i < 32; i += THREADS) {
+        twM[i] = twM_g[i];
+        twh_s[i] = twh_g[i];
+        fold_s[i] = fold_g[b * 32 + i];
+    }
+
+    while (true) {
+        __syncthreads();          // phase 2 of plane qcur is complete (first pass: the tables are in place)
+        {
+            // ---- row loop: phase 3 of plane qcur (inverse y of the class, shared -> HBM), then phase 1
+            //      of plane q (fold + forward y of the rows inside the support box, HBM -> shared)
+            float2 twr[EM], twh[EM];
+#pragma unroll
+            for (int m = 0; m < EM; ++m) { twr[m] = twM[m * LM + tM]; twh[m] = twh_s[tM + LM * m]; }
+            const TwReg<EM> tw{twr};
+            const float4 *src = X1;
+            if (q < nplanes) {
+                const int qq = q / NB;
+                const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
+                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+                src = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;    // + z*slab + y/2
+            }
+            float4 *dst = X2;
+            if (qcur >= 0) {
+                const int qq = qcur / NB;
+                const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
+                dst = X2 + (size_t)(pair * 3 + vol) * N * slab + (size_t)kx * H;       // + z*slab + tile offset
+            }
+            for (int w = warp; w < N / GM; w += NW) {
+                const int z = w * GM + gM;
+                const bool act = q < nplanes && (z + rs) % N < nzv;
+                const bool any = __any_sync(0xffffffffu, act);
+                if (qcur >= 0) {
+                    C2 v[EM];
+#pragma unroll
+                    for (int n1 = 0; n1 < EM; ++n1) v[n1] = lds_c2(plane + z * P + tM + LM * n1);
+                    fft_row_split2adj<LM, EM>(v, plane + z * P, 1, tM, tw, twh);
+                    // v[m] = (G_b[2k], G_b[2k+1]), k = tM + LM m: y pair k of class b, tile k / PPT
+#pragma unroll
+                    for (int m = 0; m < EM; ++m) {
+                        const int k = tM + LM * m;
+                        stg_c2(dst + (size_t)z * slab + ((k / PPT) * NB + b) * PPT + (k % PPT), v[m]);
+                    }
+                }
+                if (any) {
+                    C2 vn[EM];                                                         // next plane's row z
+#pragma unroll
+                    for (int n1 = 0; n1 < EM; ++n1) {
+                        const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
+                        C2 x[NB];
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) {
+                            const int f4 = idx + 32 * j;                               // y = 2 f4, 2 f4 + 1
+                            x[j] = (act && ((ymask >> (f4 >> 4)) & 1u)) ? ldg_c2(src + (size_t)z * slab + f4) : c2_zero();
+                        }
+                        C2 s;
+                        if (NB == 2) {
+                            s = b ? csub(x[0], x[1]) : cadd(x[0], x[1]);
+                        } else {
+                            if ((b & 1) == 0) {
+                                const C2 e = cadd(x[0], x[NB / 2]), o = cadd(x[1], x[NB - 1]);
+                                s = b ? csub(e, o) : cadd(e, o);
+                            } else {
+                                const C2 d0 = csub(x[0], x[NB / 2]), d1 = mul_i(csub(x[1], x[NB - 1]));
+                                s = b == 1 ? cadd(d0, d1) : csub(d0, d1);
+                            }
+                        }
+                        vn[n1] = b ? cmul(s, lds_c2(fold_s + idx)) : s;
+                    }
+                    fft_row_adj2split<LM, EM>(vn, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
+                    if (act) {
+#pragma unroll
+                        for (int m = 0; m < EM; ++m) sts_c2(plane + z * P + tM + LM * m, vn[m]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (q >= nplanes) break;
+
+        // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs k', k' + 32)
+        {
+            const int qq = q / NB;
+            const int vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
+            const float4 *Fm = (vol == 2 ? F2c : Fc) + (size_t)(kx * NB + b) * HC * N;   // + c*N + kz
+            const TwSmem<LN> tw{twN + tN};
+            for (int w = warp; w < HC / GN; w += NW) {
+                const int c = w * GN + gN;
+                C2 v[EN];
+#pragma unroll
+                for (int n1 = 0; n1 < EN; ++n1) {
+                    const int z = tN + LN * n1;
+                    const int sz = z <= N / 2 ? z : z - N;
+                    v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + c) : c2_zero();
+                }
+                if (LN >= 16) fft_pencil2_mul_late<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
+                else fft_pencil2_mul<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
+                fft_pencil2<LN, EN>(v, plane + c, P, tN, tw);
+#pragma unroll
+                for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + c, v[m]);
+            }
+        }
+        qcur = q;
+        q += gridDim.x;
+    }
+}
+
+// ------------------------------------------------------------------------------- kernel C
+// One CTA owns tile u of plane z: for every kx the NB * PPT float4 that kernel B's classes wrote
+// for y pairs u PPT .. u PPT + PPT - 1.  Per rotation pair and volume: cp.async the tile, apply
+// the radix-NB class butterfly in place (slot (b, p) -> slot (j, p) = rows n' + 64 j, n' + 64 j + 1,
+// n' = 2 (u PPT + p)), then L lanes transform one row pair along x and feed the epilogue of
+// fused_ifftx_lcc_kernel (fused.cu): ave2 kept, 1/sqrt(var) when ave arrives, LCC and the
+// running best when gcc arrives.
+template <int N>
+__global__ void __launch_bounds__(ClsCfg<N>::NB * ClsCfg<N>::PPT * ClsCfg<N>::LC, 3)
+cls_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict__ mbits,
+                     const float4 *__restrict__ fold_g, float norm, int first_index, int count,
+                     int pairs_per_chunk, int64_t *__restrict__ best, const float2 *__restrict__ twN_g) {
+    using Cfg = ClsCfg<N>;
+    constexpr int L = Cfg::LC, E = N / L, H = N / 2, NB = Cfg::NB, PPT = Cfg::PPT, NPC = NB * PPT;
+    constexpr int TP = NPC + 1, RT = 2 * NPC, BP = N + 4, THREADS = NPC * L, Q = E / L;
+    static_assert(THREADS % PPT == 0, "combine pass needs a fixed pair per thread");
+    extern __shared__ float4 smem4[];
+    float4 *tile = smem4;                                             // [N][TP]
+    float2 *lbest = reinterpret_cast<float2 *>(tile + N * TP);        // [RT][BP] (lcc, rot index bits)
+    float2 *tws = lbest + RT * BP;                                    // [E][L] W_N^(t k1)
+    const int u = blockIdx.x, z = blockIdx.y;
+    const int npairs = (count + 1) / 2;
+    const int p0 = blockIdx.z * pairs_per_chunk, p1 = min(npairs, p0 + pairs_per_chunk);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & (L - 1), pc = (32 / L) * warp + lane / L;    // pencil = tile slot pc
+    const int ya = 2 * (u * PPT + pc % PPT) + 64 * (pc / PPT);        // rows ya, ya + 1
+    const size_t slab = (size_t)N * H;
+    const size_t rowa = ((size_t)z * N + ya) * N, rowb = rowa + N;
+    float2 *lba = lbest + (2 * pc) * BP + t, *lbb = lba + BP;
+    // bit m of a row's word t: lcc_mask at x = t + L m
+    const unsigned ma = mbits[((size_t)z * N + ya) * L + t], mb = mbits[((size_t)z * N + ya + 1) * L + t];
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        lba[L * m] = make_float2(0.f, 0.f);
+        lbb[L * m] = make_float2(0.f, 0.f);
+    }
+    for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = twN_g[i];
+    const TwSmem<L> tw{tws + t};
+    // class twiddles of this thread's column of the combine pass: W_N^(n' b), W_N^((n'+1) b)
+    const int cpp = threadIdx.x % PPT;
+    C2 twc[NB - 1];
+#pragma unroll
+    for (int bb = 1; bb < NB; ++bb) twc[bb - 1] = c2_from(__ldg(fold_g + bb * 32 + u * PPT + cpp));
+    const int nitems = 3 * (p1 - p0);
+    auto prefetch = [&](int item) {
+        const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
+        const float4 *src = X2 + ((size_t)(p * 3 + vol) * N + z) * slab + u * NPC;
+        for (int idx = threadIdx.x; idx < NPC * N; idx += THREADS) {
+            const int kx = idx / NPC, c = idx % NPC;
+            cp_async16(tile + kx * TP + c, src + (size_t)kx * H + c);
+        }
+        cp_async_commit();
+    };
+    if (nitems > 0) prefetch(0);
+    C2 sd[E];
+    for (int item = 0; item < nitems; ++item) {
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---- class butterfly, in place
+        for (int idx = threadIdx.x; idx < PPT * N; idx += THREADS) {
+            float4 *e = tile + (idx / PPT) * TP + cpp;
+            C2 g[NB];
+#pragma unroll
+            for (int bb = 0; bb < NB; ++bb) g[bb] = lds_c2(e + bb * PPT);
+#pragma unroll
+            for (int bb = 1; bb < NB; ++bb) g[bb] = cmul(g[bb], twc[bb - 1]);
+            if (NB == 2) {
+                const C2 s = cadd(g[0], g[1]), d = csub(g[0], g[1]);
+                g[0] = s; g[1] = d;
+            } else {
+                dft4(g[0], g[1], g[NB / 2], g[NB - 1]);
+            }
+#pragma unroll
+            for (int bb = 0; bb < NB; ++bb) sts_c2(e + bb * PPT, g[bb]);
+        }
+        __syncthreads();
+        const int p = p0 + item / 3, vi = item % 3;
+        const uint32_t ia = (uint32_t)(first_index + 2 * p);
+        const bool have_b = 2 * p + 1 < count;
+        auto run_item = [&](auto vi_tag) {
+            constexpr int VI = decltype(vi_tag)::value;
+            {
+                C2 v[E];
+#pragma unroll
+                for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + (t + L * n1) * TP + pc);
+                pencil2_stage1<L, E>(v, tile + pc, TP, t, tw);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                C2 a[L];
+                pencil2_stage2<L>(a, tile + pc, TP, t, q);
+                if (q == Q - 1) {
+                    __syncthreads();       // every pencil is out of the tile: refill it while the arithmetic runs
+                    if (item + 1 < nitems) prefetch(item + 1);
+                }
+#pragma unroll
+                for (int k0 = 0; k0 < L; ++k0) {
+                    const int m = q + Q * k0;
+                    if (VI == 0) {
+                        sd[m] = a[k0];                                     // ave2
+                    } else if (VI == 1) {                                  // 1/sqrt(N ave2 - ave^2)
+                        const float2 vr = psub(pmul(sd[m].re, pdup(norm)), pmul(a[k0].re, a[k0].re));
+                        const float2 vq = psub(pmul(sd[m].im, pdup(norm)), pmul(a[k0].im, a[k0].im));
+                        sd[m].re = make_float2(rsqrtf(vr.x), rsqrtf(vr.y));
+                        sd[m].im = make_float2(rsqrtf(vq.x), rsqrtf(vq.y));
+                    } else {
+                        const float2 la = pmul(a[k0].re, sd[m].re), lb = pmul(a[k0].im, sd[m].im);
+                        const bool sa = have_b && (lb.x > la.x || !(la.x == la.x));
+                        const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
+                        const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
+                        const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
+                        if (((ma >> m) & 1u) && ca > lba[L * m].x) lba[L * m] = make_float2(ca, __uint_as_float(ja));
+                        if (((mb >> m) & 1u) && cb > lbb[L * m].x) lbb[L * m] = make_float2(cb, __uint_as_float(jb));
+                    }
+                }
+            }
+        };
+        if (vi == 0) run_item(std::integral_constant<int, 0>{});
+        else if (vi == 1) run_item(std::integral_constant<int, 1>{});
+        else run_item(std::integral_constant<int, 2>{});
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        if ((ma >> m) & 1u) {
+            const float2 bv = lba[L * m];
+            if (bv.x > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowa + t + L * m),
+                          (long long)pack_best(__float_as_uint(bv.x), __float_as_uint(bv.y)));
+        }
+        if ((mb >> m) & 1u) {
+            const float2 bv = lbb[L * m];
+            if (bv.x > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowb + t + L * m),
+                          (long long)pack_best(__float_as_uint(bv.x), __float_as_uint(bv.y)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- helpers
+// Fc[kx][b][c][kz] = (re F[kz][ky0][kx], re F[kz][ky1][kx], im .., im ..), ky0 = NB c + b,
+// ky1 = NB (c + 32) + b: the map spectrum in kernel B's class / column-pair order
+__global__ void cls_spectrum_kernel(const float2 *__restrict__ F, float4 *__restrict__ Fc, int N, int NB) {
+    const size_t total = (size_t)N * NB * 32 * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int kz = (int)(i % N);
+        const int c = (int)((i / N) % 32);
+        const int b = (int)((i / ((size_t)N * 32)) % NB);
+        const int kx = (int)(i / ((size_t)N * 32 * NB));
+        const float2 a = F[((size_t)kz * N + NB * c + b) * N + kx];
+        const float2 e = F[((size_t)kz * N + NB * (c + 32) + b) * N + kx];
+        Fc[i] = make_float4(a.x, e.x, a.y, e.y);
+    }
+}
+
+// mbits[row * L + t], row = z*N + y: bit m = (lcc_mask[row][t + L m] != 0) -- kernel C's lane layout
+__global__ void cls_mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint32_t *__restrict__ mbits, int N, int L,
+                                     long rows) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * L) return;
+    const long row = i / L;
+    const int t = (int)(i % L);
+    uint32_t w = 0;
+    for (int m = 0; m < N / L; ++m)
+        if (lcc_mask[row * N + t + L * m]) w |= 1u << m;
+    mbits[i] = w;
+}
+
+// ------------------------------------------------------------------------------- host side
+template <int N> static constexpr size_t smem_b_cls() {
+    return (size_t)(N + 8) * 33 * sizeof(float4) + 32 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
+}
+template <int N> static constexpr size_t smem_c_cls() {
+    using Cfg = ClsCfg<N>;
+    return (size_t)N * (Cfg::NB * Cfg::PPT + 1) * sizeof(float4) + (size_t)2 * Cfg::NB * Cfg::PPT * (N + 4) * sizeof(float2) +
+           (size_t)N * sizeof(float2);
+}
+
+static int upload_table(const std::vector<float> &h, void **out) {
+    PFB_CUDA(cudaMalloc(out, sizeof(float) * h.size()));
+    PFB_CUDA(cudaMemcpy(*out, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
+    return PFB_OK;
+}
+
+// [k1][t] = exp(+2 pi i t k1 / (lanes e))
+static std::vector<float> pencil_table(int lanes, int e) {
+    std::vector<float> h((size_t)2 * lanes * e);
+    const double n = (double)lanes * e;
+    for (int t = 0; t < lanes; ++t)
+        for (int k1 = 0; k1 < e; ++k1) {
+            const double a = 2.0 * M_PI * (double)(t * k1) / n;
+            h[2 * ((size_t)k1 * lanes + t)] = (float)cos(a);
+            h[2 * ((size_t)k1 * lanes + t) + 1] = (float)sin(a);
+        }
+    return h;
+}
+
+template <int N> static int cls_init_n(Plan *p) {
+    using Cfg = ClsCfg<N>;
+    int rc;
+    if ((rc = upload_table(pencil_table(Cfg::LN, Cfg::EN), (void **)&p->cls_twN))) return rc;
+    if ((rc = upload_table(pencil_table(4, 8), (void **)&p->cls_twM))) return rc;
+    std::vector<float> h(64), f((size_t)Cfg::NB * 32 * 4);
+    for (int k = 0; k < 32; ++k) {
+        const double a = 2.0 * M_PI * k / 64.0;
+        h[2 * k] = (float)cos(a);
+        h[2 * k + 1] = (float)sin(a);
+    }
+    for (int b = 0; b < Cfg::NB; ++b)
+        for (int i = 0; i < 32; ++i) {
+            const double a0 = 2.0 * M_PI * (double)((2 * i) * b) / N, a1 = 2.0 * M_PI * (double)((2 * i + 1) * b) / N;
+            float *o = &f[((size_t)b * 32 + i) * 4];
+            o[0] = (float)cos(a0); o[1] = (float)cos(a1); o[2] = (float)sin(a0); o[3] = (float)sin(a1);
+        }
+    if ((rc = upload_table(h, (void **)&p->cls_twh))) return rc;
+    if ((rc = upload_table(f, (void **)&p->cls_fold))) return rc;
+    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c_cls<N>()));
+    return PFB_OK;
+}
+
+int cls_init(Plan *p) { return p->nx == 256 ? cls_init_n<256>(p) : cls_init_n<128>(p); }
+
+int cls_prepare_target(Plan *p, cudaStream_t s) {
+    const int N = p->nx, NB = N / 64, L = N == 256 ? 16 : 8;
+    { LaunchScope ls(p, KC_OTHER, s);
+      cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
+    { LaunchScope ls(p, KC_OTHER, s);
+      cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N, NB); }
+    { LaunchScope ls(p, KC_OTHER, s);
+      const long rows = (long)N * N;
+      cls_mask_bits_kernel<<<(unsigned)((rows * L + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, N, L, rows); }
+    PFB_CUDA(cudaGetLastError());
+    return PFB_OK;
+}
+
+template <int N> static int cls_b_n(Plan *p, int count, float2 *X2, cudaStream_t s) {
+    using Cfg = ClsCfg<N>;
+    const int npairs = (count + 1) / 2;
+    const int nplanes = N * 3 * npairs * Cfg::NB;
+    int grid = p->sm_count * Cfg::CTAS;
+    grid -= grid % Cfg::NB;
+    grid = std::min(grid, nplanes);
+    LaunchScope ls(p, KC_FUSED_B, s);
+    cls_fftyz_mul_kernel<N><<<grid, Cfg::THREADS, smem_b_cls<N>(), s>>>(
+        reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
+        reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->cls_twN, p->cls_twM,
+        p->cls_twh, p->cls_fold, p->rs, p->ymask, p->nsig, nplanes);
+    return PFB_OK;
+}
+
+template <int N> static int cls_c_n(Plan *p, int first, int count, int rot_index_offset, int64_t *best,
+                                    const float2 *X2, cudaStream_t s) {
+    using Cfg = ClsCfg<N>;
+    constexpr int NPC = Cfg::NB * Cfg::PPT;
+    const int npairs = (count + 1) / 2;
+    const int tiles = (N / 2 / NPC) * N;
+    int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * 3 + tiles - 1) / tiles));
+    int ppc = (npairs + chunks - 1) / chunks;
+    static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
+    if (ppc_env > 0) ppc = ppc_env;
+    chunks = (npairs + ppc - 1) / ppc;
+    LaunchScope ls(p, KC_FUSED_C, s);
+    cls_ifftx_lcc_kernel<N><<<dim3(N / 2 / NPC, N, chunks), NPC * Cfg::LC, smem_c_cls<N>(), s>>>(
+        reinterpret_cast<const float4 *>(X2), p->mbits, p->cls_fold, p->norm_factor, rot_index_offset + first, count,
+        ppc, best, p->cls_twN);
+    return PFB_OK;
+}
+
+int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
+    int rc = launch_fused_a(p, first, count, s);
+    if (rc) return rc;
+    rc = p->nx == 256 ? cls_b_n<256>(p, count, X2, s) : cls_b_n<128>(p, count, X2, s);
+    if (rc) return rc;
+    PFB_CUDA(cudaGetLastError());
+    return PFB_OK;
+}
+
+int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
+    int rc = p->nx == 256 ? cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s)
+                          : cls_c_n<128>(p, first, count, rot_index_offset, best, X2, s);
+    if (rc) return rc;
+    PFB_CUDA(cudaGetLastError());
+    return PFB_OK;
+}
+
+}  // namespace pfb

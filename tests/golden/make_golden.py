@@ -153,6 +153,26 @@ def scans():
               extra=dict(subset_index=idx, seed=np.array(0)))
 
 
+def scan_256():
+    """BASELINE config 4 (subset): 256^3, Laplace + core-weighted, 6 rotations of the 4.71 deg set + 2 true poses.
+    Only eight z planes of the result grids are stored (the full grids would be 200 MB)."""
+    full = rotation_set(4.71)
+    idx = np.unique(np.r_[np.arange(0, len(full), len(full) // 5)[:5], len(full) - 1])
+    case = synth.config4(seed=0)
+    target, template, mask = f32(case.target), f32(case.template), f32(case.mask)
+    # plus the true orientations of two of the copies in the map, so that real peaks are in the grids
+    rotations = np.concatenate([full[idx[:3]], case.poses[0][0][None], full[idx[3:]], case.poses[4][0][None]])
+    lcc, rot, lcc2, c = run_reference_scan(target, template, mask, rotations, True)
+    planes = np.array([0, 1, 77, 128, 130, 201, 254, 255])
+    d = dict(rotations=rotations, laplace=np.array(1), planes=planes, seed=np.array(0), subset_index=idx,
+             lcc=lcc[planes].astype(np.float32), rot=rot[planes].astype(np.int32), lcc2=lcc2[planes].astype(np.float32),
+             lcc64_max=np.array(lcc.max()), argmax=np.array(np.unravel_index(np.argmax(lcc), lcc.shape)),
+             norm_factor=np.array(float(c._norm_factor)), rmax=np.array(int(c._rmax)),
+             lcc_mask=np.packbits(c._lcc_mask[planes].astype(bool)))
+    np.savez_compressed(os.path.join(HERE, "scan_config4_256_subset.npz"), **d)
+    print("scan_config4_256_subset R=%d lcc max %.4f at" % (len(rotations), lcc.max()), d["argmax"])
+
+
 def lcc_chain():
     """tests/test_powerfitter.py:67-79 -- perfect fit gives LCC 1 at index 0."""
     rng = np.random.default_rng(2)
@@ -169,6 +189,10 @@ def lcc_chain():
 
 
 if __name__ == "__main__":
-    rotate_vectors()
-    lcc_chain()
-    scans()
+    if len(sys.argv) > 1 and sys.argv[1] == "256":
+        scan_256()
+    else:
+        rotate_vectors()
+        lcc_chain()
+        scans()
+        scan_256()

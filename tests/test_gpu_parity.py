@@ -319,6 +319,72 @@ def test_fused_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace):
     assert np.array_equal(results["fused"][1], results["fused_noprune"][1])
 
 
+@pytest.mark.parametrize("n,cw,laplace,count", [(128, True, False, 7), (128, False, True, 6), (256, True, True, 5),
+                                                 (256, False, False, 4)])
+def test_class_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace, count):
+    """The class-decimated kernels B/C (fused_cls.cu: 256^3, and 128^3 on request) against the
+    any-shape generic pipeline, with and without support pruning, odd and even rotation counts."""
+    from powerfit_b200 import synth
+    case = synth.make_case(n=n, voxelspacing=2.8, resolution=9.0, n_res=200, rg=14.0,
+                           n_copies=3, seed=23, core_weighted=cw)
+    rots = synth.random_rotations(count, seed=6)
+    results = {}
+    for mode, env in [("generic", {"PFB_FUSED": "0"}), ("cls", {"PFB_CLS": "1"}),
+                      ("cls_noprune", {"PFB_CLS": "1", "PFB_NO_PRUNE": "1"})]:
+        for k in ("PFB_FUSED", "PFB_NO_PRUNE", "PFB_CLS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = run_scan(pfb, case.target, case.template, case.mask, rots, laplace, batch=4)
+        assert c.plan_info(6) == (0 if mode == "generic" else 1)
+        assert c.plan_info(9) == (0 if mode == "generic" else 1)
+        results[mode] = (c.lcc.copy(), c.rot.copy())
+    g_lcc, g_rot = results["generic"]
+    for mode in ("cls", "cls_noprune"):
+        lcc, rot = results[mode]
+        assert np.abs(lcc - g_lcc).max() < 2e-5, mode
+        same = rot == g_rot
+        assert same.mean() > 0.999, (mode, same.mean())
+        assert np.abs(lcc - g_lcc)[~same].max(initial=0) < 2e-5
+    assert np.array_equal(results["cls"][0], results["cls_noprune"][0])
+    assert np.array_equal(results["cls"][1], results["cls_noprune"][1])
+
+
+@pytest.mark.parametrize("name", ["scan_config2_128_subset", "scan_config3_128_cw_subset"])
+def test_class_path_128_subset_golden(pfb, monkeypatch, name):
+    """The class-decimated path at 128^3 against the reference CPU path's golden result."""
+    monkeypatch.setenv("PFB_CLS", "1")
+    g = load_golden(name)
+    target, template, mask = golden_inputs(g, name)
+    c = run_scan(pfb, target, template, mask, g["rotations"], bool(g["laplace"]))
+    assert c.plan_info(9) == 1
+    check_against_golden(c, g)
+
+
+def test_scan_256_subset_golden(pfb):
+    """BASELINE config 4 (256^3, Laplace + core-weighted) on 6 rotations of the 4.71 degree set plus two true poses,
+    against eight z planes of the reference CPU path's result."""
+    from powerfit_b200 import synth
+    g = load_golden("scan_config4_256_subset")
+    case = synth.config4(seed=int(g["seed"]))
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    c = run_scan(pfb, f32(case.target), f32(case.template), f32(case.mask), g["rotations"], True)
+    assert c.plan_info(6) == 1 and c.plan_info(9) == 1
+    assert c._rmax == int(g["rmax"]) and float(c._norm_factor) == float(g["norm_factor"])
+    planes = g["planes"]
+    lcc, rot = c.lcc[planes], c.rot[planes]
+    assert np.isfinite(lcc).all()
+    err = np.abs(lcc - g["lcc"]).max()
+    assert err <= LCC_TOL, err
+    decided = (g["lcc"] - g["lcc2"]) > LCC_TOL
+    assert decided.sum() > 1000
+    assert np.array_equal(rot[decided], g["rot"][decided])
+    lm = np.unpackbits(g["lcc_mask"])[:lcc.size].reshape(lcc.shape).astype(bool)
+    assert (lcc[~lm] == 0).all() and (rot[~lm] == 0).all()
+    assert tuple(np.unravel_index(np.argmax(c.lcc), c.lcc.shape)) == tuple(int(v) for v in g["argmax"])
+    assert abs(float(c.lcc.max()) - float(g["lcc64_max"])) <= LCC_TOL
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["scan_config1_64", "scan_32_plain", "scan_24_laplace_cw",
                                   "scan_config2_128_subset", "rough"])
