@@ -156,7 +156,6 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;
     if (p->fused) {
         p->cls = nx == 256;
-        if (const char *e = getenv("PFB_CLS")) p->cls = p->cls || (nx == 128 && atoi(e) != 0);
         PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
         PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 16);

@@ -117,6 +117,7 @@ struct Plan {
     unsigned ymask = 0;
     // class-decimated variant of kernels B and C (fused_cls.cu)
     bool cls = false;
+    unsigned nmask = 0;                            // tiles of 4 folded rows n (n = y mod 64) that meet the support
     float2 *cls_twN = nullptr, *cls_twM = nullptr, *cls_twh = nullptr;
     float4 *cls_fold = nullptr;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]

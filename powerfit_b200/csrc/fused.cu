@@ -499,7 +499,6 @@ template <int N> static int fused_init_n(Plan *p) {
     constexpr int TP = 33;
     PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    if (p->cls) return cls_init(p);
     PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_b<N>()));
     if (N >= 128)
@@ -517,8 +516,6 @@ bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (n
 int fused_init(Plan *p) {
     if (p->nx == 64) return fused_init_n<64>(p);
     if (p->nx == 128) return fused_init_n<128>(p);
-    PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * 256 * 33 * sizeof(float2))));
     return cls_init(p);
 }
 
@@ -565,6 +562,12 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
             if (sy >= -p->rs && sy <= p->rs) ymask |= 1u << tile;
         }
     p->ymask = ymask;
+    unsigned nmask = 0;
+    for (int y = 0; y < N; ++y) {
+        const int sy = y <= N / 2 ? y : y - N;
+        if (sy >= -p->rs && sy <= p->rs) nmask |= 1u << ((y % 64) / 4);
+    }
+    p->nmask = nmask;
     return PFB_OK;
 }
 
@@ -583,8 +586,7 @@ static int fused_a_n(Plan *p, int first, int count, cudaStream_t s) {
 
 int launch_fused_a(Plan *p, int first, int count, cudaStream_t s) {
     if (p->nx == 64) return fused_a_n<64, 8>(p, first, count, s);
-    if (p->nx == 128) return fused_a_n<128, 8>(p, first, count, s);
-    return fused_a_n<256, 16>(p, first, count, s);
+    return fused_a_n<128, 8>(p, first, count, s);
 }
 
 // front half of a batch: A (rotate + x) and B (y, z, multiply, z, y) into the work buffer X2

@@ -1,26 +1,27 @@
 // Class-decimated fused pipeline for cubic grids whose (y,z) plane does not fit one SM's shared
-// memory (N = 256; selectable for N = 128).  Same three kernels as fused.cu,
+// memory (N = 256).  Same three kernels as fused.cu,
 //
-//   A  fused_rotate_fftx   (fused.cu)  rotate + forward x            -> X1[pair][sig][z][kx][y]
-//   B  cls_fftyz_mul                   forward y,z * FT(map), inverse z,y of ONE ky class
-//   C  cls_ifftx_lcc                   class combine, inverse x, LCC, running best
+//   A  cls_rotate_fftx   rotate + forward x + class fold        -> X1[pair][sig][z][kx][b][n]
+//   B  cls_fftyz_mul     forward y,z * FT(map), inverse z,y of ONE ky class
+//   C  cls_ifftx_lcc     class combine, inverse x, LCC, running best
 //
-// but kernel B works on a quarter (N = 256) or half (N = 128) of a (y,z) plane:
-// with NB = N/64 and ky = NB k' + b the first radix-NB step of a decimation-in-frequency
-// y transform splits the outputs into NB residue classes b, each a 64-point transform of the
-// folded row   g_b[n] = W_N^(n b) sum_j x[n + 64 j] W_NB^(j b),   n < 64.
-// The z transforms, the multiplication with the map spectrum and the inverse z transforms act
-// on every ky column on its own, so a CTA that owns class b of plane kx needs only the
-// N x 64 tile of its class (132 KB at N = 256) -- at the price of reading the (support-pruned,
-// L2-resident) input rows NB times.  The inverse y transform of class b yields
+// but kernel B works on a quarter of a (y,z) plane: with NB = N/64 and ky = NB k' + b the first
+// radix-NB step of a decimation-in-frequency y transform splits the outputs into NB residue
+// classes b, each a 64-point transform of the folded row
+//   g_b[n] = W_N^(n b) sum_j x[n + 64 j] W_NB^(j b),   n < 64.
+// The fold acts per (z, kx), so it commutes with the x transform: kernel A, whose tile holds
+// the rows n + 64 j of a few n, applies it before it stores.  The z transforms, the
+// multiplication with the map spectrum and the inverse z transforms act on every ky column on
+// its own, so a CTA that owns class b of plane kx needs only the N x 64 tile of its class
+// (132 KB at N = 256).  The inverse y transform of class b yields
 //   G_b[n'] = sum_k' X[NB k' + b] W_64^(n' k'),   y[n' + 64 j] = sum_b W_NB^(j b) W_N^(n' b) G_b[n'],
-// and that last radix-NB butterfly is linear and acts per (z, kx), so it commutes with the
-// inverse x transform: kernel B stores G_b, and kernel C applies the butterfly to its tile in
-// shared memory before the x pencils run.  HBM traffic stays at the three-kernel minimum
-// (n_f S pruned + 3 S + 3 S per rotation); nothing is written that the 128^3 pipeline would
-// not write.  (K numbers / reference lines: see fused.cu.)
+// and that last radix-NB butterfly again acts per (z, kx) and commutes with the inverse x
+// transform: kernel B stores G_b, and kernel C applies the butterfly to its tile in shared
+// memory before the x pencils run.  HBM traffic stays at the three-kernel minimum (n_f S
+// pruned in z + 3 S + 3 S per rotation).  (K numbers / reference lines: see fused.cu.)
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "rotate_device.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -32,8 +33,129 @@ namespace pfb {
 template <int N> struct ClsCfg;
 // LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
 // class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows)
-template <> struct ClsCfg<128> { static constexpr int LN = 8, EN = 16, THREADS = 256, CTAS = 2, NB = 2, PPT = 8, LC = 8; };
 template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16; };
+
+// ------------------------------------------------------------------------------- kernel A
+// CTA = (z, tile of RN values of n, rotation pair); its NB RN rows are y = n + 64 j.  Gather
+// (as fused_rotate_fftx_kernel), x transform with 16 lanes per row, then per (kx, n) the
+// radix-NB fold over j with the class twiddles, stored as y pairs (g_b[n], g_b[n+1]).
+template <int N, bool CORNER, bool STREAM>
+__global__ void __launch_bounds__(256, 2)
+cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ tmpl, const float *__restrict__ mask,
+                       const double *__restrict__ rot, int first, int count, int nsig,
+                       float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
+                       unsigned nmask, int nzv) {
+    constexpr int L = 16, E = N / L, NB = N / 64, RN = 4, ROWS = NB * RN, TP = ROWS + 1, THREADS = ROWS * L;
+    static_assert(THREADS == 256 && NB == 4, "N = 256");
+    extern __shared__ float2 smem[];
+    float2 *tile_t = smem, *tile_m = smem + N * TP;
+    const int pair = blockIdx.y;
+    const int j = blockIdx.x % nzv;
+    int nt_rank = blockIdx.x / nzv, ntile = 0;
+    for (unsigned mbits = nmask;; ++ntile) {
+        if (mbits & 1u) { if (nt_rank == 0) break; --nt_rank; }
+        mbits >>= 1;
+    }
+    const int z = (j - rs + N) % N, n0 = RN * ntile;
+    const GridDims d{N, N, N, N / 2, (long)N * N * N};
+    const int ra = first + 2 * pair;
+    const bool have_b = 2 * pair + 1 < count;
+    const double *Ra = rot + (long)ra * 9, *Rb = Ra + 9;
+    const int oz = z <= N / 2 ? z : z - N;
+
+    for (int idx = threadIdx.x; idx < N * TP; idx += THREADS) {
+        tile_t[idx] = make_float2(0.f, 0.f);
+        tile_m[idx] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int xlo = max(-rs, -(N / 2 - 1)), W = rs - xlo + 1;
+    const int lim2 = min(rs2, (N / 2) * (N / 2));
+#pragma unroll 2
+    for (int idx = threadIdx.x; idx < ROWS * W; idx += THREADS) {
+        const int rr = idx / W, ox = idx % W + xlo;
+        const int iy = n0 + rr % RN + 64 * (rr / RN);
+        const int oy = iy <= N / 2 ? iy : iy - N;
+        // offset -N/2 aliases index N/2, which belongs to offset +N/2
+        if (oy > -(N / 2) && ox * ox + oy * oy + oz * oz <= lim2) {
+            float2 tv = make_float2(0.f, 0.f), mv = make_float2(0.f, 0.f);
+            const SrcCoord ca = source_coord(Ra, ox, oy, oz);
+            tv.x = CORNER ? sample_trilinear_q(tmplq, d, ca) : sample_trilinear(tmpl, d, ca);
+            mv.x = sample_nearest(mask, d, ca);
+            if (have_b) {
+                const SrcCoord cb = source_coord(Rb, ox, oy, oz);
+                tv.y = CORNER ? sample_trilinear_q(tmplq, d, cb) : sample_trilinear(tmpl, d, cb);
+                mv.y = sample_nearest(mask, d, cb);
+            }
+            const int x = ox < 0 ? ox + N : ox;
+            tile_t[x * TP + rr] = tv;
+            tile_m[x * TP + rr] = mv;
+        }
+    }
+    __syncthreads();
+
+    // ---- x transforms: thread (row rr, t)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & (L - 1), rr = 2 * warp + lane / L;
+    float2 tw[E];
+    load_twiddles<E>(tw, twN, t);
+    float2 v[E], v2[E];
+#pragma unroll
+    for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
+    fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
+#pragma unroll
+    for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
+#pragma unroll
+    for (int n1 = 0; n1 < E; ++n1) {
+        v[n1] = tile_m[(t + L * n1) * TP + rr];
+        v2[n1] = make_float2(v[n1].x * v[n1].x, v[n1].y * v[n1].y);
+    }
+    fft_pencil<E, L>(v, tile_m + rr, TP, t, tw, true);
+#pragma unroll
+    for (int m = 0; m < E; ++m) tile_m[(t + L * m) * TP + rr] = v[m];
+    __syncthreads();
+
+    // ---- fold over j and store: thread (kx, pair slot ps): rows r = 2 ps, 2 ps + 1
+    constexpr int H = N / 2, PS = RN / 2;
+    const size_t slab = (size_t)N * H;
+    float4 *X14 = reinterpret_cast<float4 *>(X1);
+    const int ps = threadIdx.x % PS;
+    float2 wf[2][NB - 1];                                    // W_N^((n0 + r) b), b = 1..NB-1
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int b = 1; b < NB; ++b) wf[e][b - 1] = __ldg(twN + ((n0 + 2 * ps + e) * b) % N);
+    auto fold_store = [&](const float2 *tile, int sig) {
+        float4 *o = X14 + ((size_t)(pair * nsig + sig) * N + z) * slab + n0 / 2 + ps;     // + kx*H + b*32
+        for (int idx = threadIdx.x; idx < PS * N; idx += THREADS) {
+            const int kx = idx / PS;
+            float2 g[2][NB];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) g[e][jj] = tile[kx * TP + 2 * ps + e + RN * jj];
+                dft4(g[e][0], g[e][1], g[e][2], g[e][3]);
+#pragma unroll
+                for (int b = 1; b < NB; ++b) g[e][b] = cmulf(g[e][b], wf[e][b - 1]);
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float4 val = make_float4(g[0][b].x, g[1][b].x, g[0][b].y, g[1][b].y);
+                if (STREAM) __stcs(o + (size_t)kx * H + b * 32, val);
+                else o[(size_t)kx * H + b * 32] = val;
+            }
+        }
+    };
+    fold_store(tile_t, 0);
+    fold_store(tile_m, 1);
+    if (nsig == 3) {
+        __syncthreads();
+        fft_pencil<E, L>(v2, tile_t + rr, TP, t, tw, true);
+#pragma unroll
+        for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v2[m];
+        __syncthreads();
+        fold_store(tile_t, 2);
+    }
+}
 
 // ------------------------------------------------------------------------------- kernel B
 // Plane q = ((kx * 3 + volume) * npairs + pair) * NB + b; the grid is a multiple of NB, so a
@@ -45,7 +167,7 @@ __global__ void __launch_bounds__(ClsCfg<N>::THREADS, ClsCfg<N>::CTAS)
 cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fc,
                      const float4 *__restrict__ F2c, const float2 *__restrict__ twN_g,
                      const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g,
-                     const float4 *__restrict__ fold_g, int rs, unsigned ymask, int nsig, int nplanes) {
+                     int rs, unsigned nmask, int nsig, int nplanes) {
     using Cfg = ClsCfg<N>;
     constexpr int H = N / 2, HC = 32, P = 33, NB = Cfg::NB, PPT = Cfg::PPT;
     constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
@@ -54,8 +176,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                        // [N][P]
     float4 *dummy = plane + N * P;                                // [GM][P] scratch rows of idle lanes
-    float4 *fold_s = dummy + GM * P;                              // [32] W_N^(n b), n = 2 idx, 2 idx + 1
-    float2 *twN = reinterpret_cast<float2 *>(fold_s + 32);        // [EN][LN] W_N^(t k1)
+    float2 *twN = reinterpret_cast<float2 *>(dummy + GM * P);     // [EN][LN] W_N^(t k1)
     float2 *twM = twN + N;                                        // [EM][LM] W_32^(t k1)
     float2 *twh_s = twM + 32;                                     // [32] W_64^k of the split radix-2 step
     const size_t slab = (size_t)N * H;                            // float4 per z of X1 / X2
@@ -74,14 +195,13 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
     for (int i = threadIdx.x; i < 32; i += THREADS) {
         twM[i] = twM_g[i];
         twh_s[i] = twh_g[i];
-        fold_s[i] = fold_g[b * 32 + i];
     }
 
     while (true) {
         __syncthreads();          // phase 2 of plane qcur is complete (first pass: the tables are in place)
         {
             // ---- row loop: phase 3 of plane qcur (inverse y of the class, shared -> HBM), then phase 1
-            //      of plane q (fold + forward y of the rows inside the support box, HBM -> shared)
+            //      of plane q (forward y of the folded rows inside the support box, HBM -> shared)
             float2 twr[EM], twh[EM];
 #pragma unroll
             for (int m = 0; m < EM; ++m) { twr[m] = twM[m * LM + tM]; twh[m] = twh_s[tM + LM * m]; }
@@ -91,7 +211,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                 const int qq = q / NB;
                 const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
                 const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
-                src = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;    // + z*slab + y/2
+                src = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H + b * 32;   // + z*slab + n/2
             }
             float4 *dst = X2;
             if (qcur >= 0) {
@@ -120,25 +240,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) {
                         const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
-                        C2 x[NB];
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) {
-                            const int f4 = idx + 32 * j;                               // y = 2 f4, 2 f4 + 1
-                            x[j] = (act && ((ymask >> (f4 >> 4)) & 1u)) ? ldg_c2(src + (size_t)z * slab + f4) : c2_zero();
-                        }
-                        C2 s;
-                        if (NB == 2) {
-                            s = b ? csub(x[0], x[1]) : cadd(x[0], x[1]);
-                        } else {
-                            if ((b & 1) == 0) {
-                                const C2 e = cadd(x[0], x[NB / 2]), o = cadd(x[1], x[NB - 1]);
-                                s = b ? csub(e, o) : cadd(e, o);
-                            } else {
-                                const C2 d0 = csub(x[0], x[NB / 2]), d1 = mul_i(csub(x[1], x[NB - 1]));
-                                s = b == 1 ? cadd(d0, d1) : csub(d0, d1);
-                            }
-                        }
-                        vn[n1] = b ? cmul(s, lds_c2(fold_s + idx)) : s;
+                        vn[n1] = (act && ((nmask >> (idx >> 1)) & 1u)) ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
                     }
                     fft_row_adj2split<LM, EM>(vn, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
                     if (act) {
@@ -346,8 +448,9 @@ __global__ void cls_mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint3
 }
 
 // ------------------------------------------------------------------------------- host side
+template <int N> static constexpr size_t smem_a_cls() { return (size_t)2 * N * (4 * (N / 64) + 1) * sizeof(float2); }
 template <int N> static constexpr size_t smem_b_cls() {
-    return (size_t)(N + 8) * 33 * sizeof(float4) + 32 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
+    return (size_t)(N + 8) * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
 }
 template <int N> static constexpr size_t smem_c_cls() {
     using Cfg = ClsCfg<N>;
@@ -393,6 +496,10 @@ template <int N> static int cls_init_n(Plan *p) {
         }
     if ((rc = upload_table(h, (void **)&p->cls_twh))) return rc;
     if ((rc = upload_table(f, (void **)&p->cls_fold))) return rc;
+    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
     PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_b_cls<N>()));
     PFB_CUDA(cudaFuncSetAttribute(cls_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -400,10 +507,10 @@ template <int N> static int cls_init_n(Plan *p) {
     return PFB_OK;
 }
 
-int cls_init(Plan *p) { return p->nx == 256 ? cls_init_n<256>(p) : cls_init_n<128>(p); }
+int cls_init(Plan *p) { return cls_init_n<256>(p); }
 
 int cls_prepare_target(Plan *p, cudaStream_t s) {
-    const int N = p->nx, NB = N / 64, L = N == 256 ? 16 : 8;
+    const int N = p->nx, NB = N / 64, L = ClsCfg<256>::LC;
     { LaunchScope ls(p, KC_OTHER, s);
       cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
     { LaunchScope ls(p, KC_OTHER, s);
@@ -426,7 +533,7 @@ template <int N> static int cls_b_n(Plan *p, int count, float2 *X2, cudaStream_t
     cls_fftyz_mul_kernel<N><<<grid, Cfg::THREADS, smem_b_cls<N>(), s>>>(
         reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
         reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->cls_twN, p->cls_twM,
-        p->cls_twh, p->cls_fold, p->rs, p->ymask, p->nsig, nplanes);
+        p->cls_twh, p->rs, p->nmask, p->nsig, nplanes);
     return PFB_OK;
 }
 
@@ -448,18 +555,30 @@ template <int N> static int cls_c_n(Plan *p, int first, int count, int rot_index
     return PFB_OK;
 }
 
+template <int N> static int cls_a_n(Plan *p, int first, int count, cudaStream_t s) {
+    const int npairs = (count + 1) / 2;
+    const int nzv = std::min(2 * p->rs + 1, N);
+    const int ntl = __builtin_popcount(p->nmask);
+    LaunchScope ls(p, KC_FUSED_A, s);
+    static const int mode = getenv("PFB_A_MODE") ? atoi(getenv("PFB_A_MODE")) : 3;   // bit 0: corner table, bit 1: streaming stores
+    auto kern = mode == 3 ? cls_rotate_fftx_kernel<N, true, true> : mode == 2 ? cls_rotate_fftx_kernel<N, false, true>
+              : mode == 1 ? cls_rotate_fftx_kernel<N, true, false> : cls_rotate_fftx_kernel<N, false, false>;
+    kern<<<dim3(nzv * ntl, npairs), 256, smem_a_cls<N>(), s>>>(
+        p->tmplq, p->tmpl, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->nmask, nzv);
+    return PFB_OK;
+}
+
 int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
-    int rc = launch_fused_a(p, first, count, s);
+    int rc = cls_a_n<256>(p, first, count, s);
     if (rc) return rc;
-    rc = p->nx == 256 ? cls_b_n<256>(p, count, X2, s) : cls_b_n<128>(p, count, X2, s);
+    rc = cls_b_n<256>(p, count, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
 int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
-    int rc = p->nx == 256 ? cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s)
-                          : cls_c_n<128>(p, first, count, rot_index_offset, best, X2, s);
+    int rc = cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
