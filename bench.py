@@ -5,7 +5,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" scans one block of `--rot-per-step` rotations per GPU (weak scaling: every rank
+A "step" scans one block of `--rot-per-step` rotations per GPU (default at 128^3: the whole 7416-rotation
+10 degree search; weak scaling: every rank
 gets its own block of that size) into the device-resident packed best grid; at N > 1 the
 step ends with the packed MAX all-reduce that merges the ranks' grids.  `value` is
 rotations/s over all ranks with inputs resident in HBM; `e2e` is the same metric through
@@ -199,7 +200,8 @@ def main():
     case = make_inputs(args.workload)
     n = w["n"]
     V = n ** 3
-    rps = args.rot_per_step or {64: 2048, 128: 512, 256: 64}.get(n, 256)
+    # one step = one full rotational search of the named angle at 128^3 (7416 rotations); bounded blocks elsewhere
+    rps = args.rot_per_step or {64: 2048, 128: w["full_R"], 256: 128}.get(n, 256)
     total_steps = args.warmup + args.steps
     rots = synth.random_rotations(rps * total_steps * world + 8, seed=1)
 
@@ -301,11 +303,20 @@ def main():
            "rotate": nf * S, "fft_x": (2 * nf + 6) * S, "fft_y": (2 * nf + 6) * S, "fft_z": (2 * nf + 6) * S,
            "multiply": (nf + 3) * S, "lcc_best": 3 * S}
     roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "traffic_source": None,
             "step_achieved": value / world * B_rot / 1e9, "step_frac": value / world * B_rot / 1e9 / peak,
             "bytes_per_rotation": B_rot}
     if top:
         k = kernels[top]
         ach = alg.get(top, 0) * rps / (k["ms"] / 1e3) / 1e9
+        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch of that
+        # capture's batch, rescaled to this run's batch); null if there is no capture for this workload
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload][top]
+            roof["traffic"] = tr["dram_bytes_per_launch"] * corr.plan_info(4) / tr["batch"]
+            roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         roof.update({"kernel": top, "achieved": ach, "frac": ach / peak,
                      "kernel_share_of_step": k["ms"] / tot_ms,
                      "kernel_ms_per_launch": k["ms"] / k["launches"],
