@@ -209,7 +209,7 @@ def main():
     corr.template = case.template
     corr.mask = case.mask
     corr.rotations = rots
-    nf = 2 if bool(np.all(corr._mask[corr._mask != 0] == 1.0)) else 3
+    nf = 2 if corr._mask_binary else 3
     S = 8 * n * n * (n // 2 + 1)
     B_rot = (2 * nf + 6) * S
     stream = torch.cuda.current_stream(dev)

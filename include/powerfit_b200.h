@@ -71,6 +71,21 @@ int pfb_set_target(pfb_plan *plan, const float *target, const uint8_t *lcc_mask,
 int pfb_set_template(pfb_plan *plan, const float *tmpl, const float *mask, float norm_factor,
                      int mask_is_binary, void *stream);
 
+/* The same two setters with the reference's one-time preparation done on the device in FP64
+ * (SURVEY.md 8f rows N3/N2).  All pointers DEVICE unless noted.
+ * pfb_prepare_target = BaseCorrelator.__init__ + GPUCorrelator.__init__ (powerfitter.py:169-180,
+ * 410-414): f = target / target.max(); lcc_mask = f > 0.05 f.max(); [scipy.ndimage.laplace(f,
+ * mode='wrap')]; float32 cast -> f_out, lcc_mask_out (both kept by the caller), then pfb_set_target.
+ * Bit-identical to the numpy/scipy formulas.
+ * pfb_prepare_template = BaseCorrelator.mask.fset (powerfitter.py:190-220): N = count(mask != 0)
+ * -> *norm_factor (HOST); [Laplace]; t *= m; z-score over mask != 0; t *= m; float32 casts ->
+ * t_out, m_out; *mask_is_binary (HOST) = all(mask[mask != 0] == 1); then pfb_set_template.
+ * Synchronises the stream.  PFB_ERR_INVALID "Zero-filled mask is not allowed." like :201-202. */
+int pfb_prepare_target(pfb_plan *plan, const double *target, int laplace, float *f_out,
+                       uint8_t *lcc_mask_out, void *stream);
+int pfb_prepare_template(pfb_plan *plan, const double *tmpl, const double *mask, int laplace, float *t_out,
+                         float *m_out, double *norm_factor, int *mask_is_binary, void *stream);
+
 /* Reset a packed best grid to "LCC 0, rotation 0" (glcc.fill(0), grot.fill(0),
  * powerfitter.py:516-517). best = nz*ny*nx int64 packed keys: (orderable(lcc) << 32) | (0xFFFFFFFF - rot), signed order. */
 int pfb_best_init(pfb_plan *plan, int64_t *best, void *stream);

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 SYMBOLS = ["pfb_version", "pfb_last_error", "pfb_plan_create", "pfb_plan_destroy", "pfb_plan_info",
            "pfb_set_target", "pfb_set_template", "pfb_best_init", "pfb_scan", "pfb_unpack",
            "pfb_merge_best", "pfb_profile", "pfb_profile_read", "pfb_rotate", "pfb_fft3_c2c", "pfb_lcc_take_best", "pfb_search_host",
-           "pfb_lcc_max", "pfb_peak_candidates"]
+           "pfb_lcc_max", "pfb_peak_candidates", "pfb_prepare_target", "pfb_prepare_template"]
 
 _lib = None
 
@@ -74,6 +74,8 @@ def load():
     lib.pfb_plan_info.argtypes = [vp, i32, c.POINTER(c.c_int64)]
     lib.pfb_set_target.argtypes = [vp, vp, vp, vp]
     lib.pfb_set_template.argtypes = [vp, vp, vp, f32, i32, vp]
+    lib.pfb_prepare_target.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.pfb_prepare_template.argtypes = [vp, vp, vp, i32, vp, vp, c.POINTER(c.c_double), c.POINTER(i32), vp]
     lib.pfb_best_init.argtypes = [vp, vp, vp]
     lib.pfb_scan.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.pfb_unpack.argtypes = [vp, vp, vp, vp, vp]

@@ -7,9 +7,12 @@ the target array (+ a device handle + ``laplace``), then ``.template``, ``.mask`
 (float32) / ``.rot`` (int32) hold the results.  The same ``ValueError`` messages are
 raised for the same contract violations.
 
-One-time host preparation (target normalisation, lcc_mask, Laplace filter, template
-z-scoring) follows the reference formulas in FP64 numpy and is then cast to FP32, like
-``GPUCorrelator`` does (powerfitter.py:414, 471-474).  Everything per-rotation runs in
+One-time preparation (target normalisation, lcc_mask, Laplace filter, template
+z-scoring) follows the reference formulas in FP64 and is then cast to FP32, like
+``GPUCorrelator`` does (powerfitter.py:414, 471-474).  By default it runs on the device
+(``pfb_prepare_target`` / ``pfb_prepare_template``: the FP64 arrays are uploaded as they
+are); ``prep="host"`` keeps the numpy/scipy formulation, which the tests use as the
+cross-check of the device kernels.  Everything per-rotation runs in
 the hand-written sm_100a kernels behind the C ABI (``include/powerfit_b200.h``);
 PyTorch only provides device buffers, the stream and -- when a process group is
 initialised -- the single MAX all-reduce that merges the rotation shards.
@@ -62,21 +65,27 @@ def _resolve_device(device):
 class CUDACorrelator(object):
     """B200 implementation of the local cross-correlation search."""
 
-    def __init__(self, target, device=None, laplace=False, batch=0):
+    def __init__(self, target, device=None, laplace=False, batch=0, prep="device"):
         import torch
         self._torch = torch
         self._libh = _lib.load()
         target = np.asarray(target, dtype=np.float64)
         if target.ndim != 3:
             raise ValueError("target must be a 3-D array")
-        # BaseCorrelator.__init__, powerfitter.py:169-176
-        self._target = target / target.max()
+        if prep not in ("device", "host"):
+            raise ValueError("prep must be 'device' or 'host'")
+        self._prep = prep
+        self._target_in = target                       # normalised lazily (property _target)
+        self._shape = target.shape
+        self._target_h = None
+        self._lcc_mask_h = None
         self._rotations = None
-        self._template = None
+        self._template_h = None
+        self._template_set = False
         self._mask = None
+        self._mask_binary = None
         self._laplace = laplace
-        self._lcc_mask = (self._target > self._target.max() * 0.05).astype(np.uint8)
-        self._rmax = min(target.shape) // 2
+        self._rmax = min(target.shape) // 2            # powerfitter.py:176
         self._lcc = None
         self._rot = None
         self.progress = False
@@ -88,13 +97,49 @@ class CUDACorrelator(object):
         nz, ny, nx = target.shape
         _lib.check(self._libh.pfb_plan_create(nz, ny, nx, int(batch), self._device.index,
                                               ctypes.byref(self._plan)))
-        t = _laplace_wrap(self._target) if laplace else self._target      # powerfitter.py:410-412
         with torch.cuda.device(self._device):
-            self._d_target = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(self._device)
-            self._d_lcc_mask = torch.from_numpy(np.ascontiguousarray(self._lcc_mask)).to(self._device)
             self._best = torch.empty(target.size, dtype=torch.int64, device=self._device)
-            _lib.check(self._libh.pfb_set_target(self._plan, self._d_target.data_ptr(),
-                                                 self._d_lcc_mask.data_ptr(), self._stream()))
+            if prep == "device":
+                # BaseCorrelator.__init__ + GPUCorrelator.__init__ (powerfitter.py:169-180, 410-414) in FP64 kernels
+                d64 = torch.from_numpy(np.ascontiguousarray(target)).to(self._device)
+                self._d_target = torch.empty(target.shape, dtype=torch.float32, device=self._device)
+                self._d_lcc_mask = torch.empty(target.shape, dtype=torch.uint8, device=self._device)
+                _lib.check(self._libh.pfb_prepare_target(self._plan, d64.data_ptr(), int(bool(laplace)),
+                                                         self._d_target.data_ptr(), self._d_lcc_mask.data_ptr(),
+                                                         self._stream()))
+                torch.cuda.current_stream(self._device).synchronize()
+            else:
+                t = _laplace_wrap(self._target) if laplace else self._target      # powerfitter.py:410-412
+                self._d_target = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(self._device)
+                self._d_lcc_mask = torch.from_numpy(np.ascontiguousarray(self._lcc_mask)).to(self._device)
+                _lib.check(self._libh.pfb_set_target(self._plan, self._d_target.data_ptr(),
+                                                     self._d_lcc_mask.data_ptr(), self._stream()))
+
+    # host views of the prepared inputs, materialised on first use
+    @property
+    def _target(self):                                 # powerfitter.py:170
+        if self._target_h is None:
+            self._target_h = self._target_in / self._target_in.max()
+        return self._target_h
+
+    @property
+    def _lcc_mask(self):                               # powerfitter.py:178-180
+        if self._lcc_mask_h is None:
+            if self._prep == "device":
+                self._lcc_mask_h = self._d_lcc_mask.cpu().numpy()
+            else:
+                self._lcc_mask_h = (self._target > self._target.max() * 0.05).astype(np.uint8)
+        return self._lcc_mask_h
+
+    @property
+    def _template(self):
+        if self._template_h is None and self._template_set and self._prep == "device" and self._mask is not None:
+            self._template_h = self._d_template.cpu().numpy().astype(np.float64)
+        return self._template_h
+
+    @_template.setter
+    def _template(self, value):
+        self._template_h = value
 
     def __del__(self):
         try:
@@ -128,9 +173,10 @@ class CUDACorrelator(object):
     @template.setter
     def template(self, template):                      # powerfitter.py:236-243
         template = np.asarray(template)
-        if template.shape != self._target.shape:
+        if template.shape != self._shape:
             raise ValueError("Shape of template does not match the target.")
         self._mask = None
+        self._template_set = True
         self._template = np.array(template, dtype=np.float64)
 
     @property
@@ -139,28 +185,49 @@ class CUDACorrelator(object):
 
     @mask.setter
     def mask(self, mask):                              # powerfitter.py:190-210, 466-474
-        if self._template is None:
+        if not self._template_set:
             raise ValueError("First set the template.")
         mask = np.asarray(mask)
-        if self._target.shape != mask.shape:
+        if self._shape != mask.shape:
             raise ValueError("Shape of the mask is different from target.")
+        torch = self._torch
+        if self._prep == "device":
+            m64 = np.array(mask, dtype=np.float64)
+            with torch.cuda.device(self._device):
+                d_t64 = torch.from_numpy(np.ascontiguousarray(self._template)).to(self._device)
+                d_m64 = torch.from_numpy(m64).to(self._device)
+                self._d_template = torch.empty(self._shape, dtype=torch.float32, device=self._device)
+                self._d_mask = torch.empty(self._shape, dtype=torch.float32, device=self._device)
+                nf, binary = ctypes.c_double(), ctypes.c_int()
+                _lib.check(self._libh.pfb_prepare_template(
+                    self._plan, d_t64.data_ptr(), d_m64.data_ptr(), int(bool(self._laplace)),
+                    self._d_template.data_ptr(), self._d_mask.data_ptr(), ctypes.byref(nf), ctypes.byref(binary),
+                    self._stream()))
+                torch.cuda.current_stream(self._device).synchronize()
+            self._norm_factor = int(nf.value)
+            self._mask_binary = bool(binary.value)
+            self._mask = m64
+            self._template_h = None                    # prepared template: fetched from the device on demand
+            return
         ind = mask != 0
         self._norm_factor = ind.sum()
         if self._norm_factor == 0:
             raise ValueError("Zero-filled mask is not allowed.")
         self._mask = np.array(mask, dtype=np.float64)
+        t = self._template
         if self._laplace:
-            self._template = _laplace_wrap(self._template)
-        self._template *= self._mask
-        self._template[ind] -= self._template[ind].mean()       # powerfitter.py:217-220
-        self._template[ind] /= self._template[ind].std()
-        self._template *= self._mask
+            t = _laplace_wrap(t)
+        t *= self._mask
+        t[ind] -= t[ind].mean()                        # powerfitter.py:217-220
+        t[ind] /= t[ind].std()
+        t *= self._mask
+        self._template_h = t
         binary = bool(np.all(self._mask[ind] == 1.0))
-        torch = self._torch
+        self._mask_binary = binary
         with torch.cuda.device(self._device):
-            d_t = torch.from_numpy(np.ascontiguousarray(self._template, dtype=np.float32)).to(self._device)
-            d_m = torch.from_numpy(np.ascontiguousarray(self._mask, dtype=np.float32)).to(self._device)
-            _lib.check(self._libh.pfb_set_template(self._plan, d_t.data_ptr(), d_m.data_ptr(),
+            self._d_template = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(self._device)
+            self._d_mask = torch.from_numpy(np.ascontiguousarray(self._mask, dtype=np.float32)).to(self._device)
+            _lib.check(self._libh.pfb_set_template(self._plan, self._d_template.data_ptr(), self._d_mask.data_ptr(),
                                                    float(self._norm_factor), int(binary), self._stream()))
             torch.cuda.current_stream(self._device).synchronize()
 
@@ -185,7 +252,7 @@ class CUDACorrelator(object):
     def scan_device(self, lo=None, hi=None, reset=True):
         """Run rotations [lo, hi) (global indices) into the device-resident packed best
         grid; no host transfer except the rotation matrices.  Returns the int64 tensor."""
-        if any(req is None for req in (self._template, self._mask, self._rotations)):
+        if not self._template_set or self._mask is None or self._rotations is None:
             raise ValueError("First set the template, mask, and rotations.")
         nrot = self._rotations.shape[0]
         lo = 0 if lo is None else lo
@@ -230,8 +297,8 @@ class CUDACorrelator(object):
         if world > 1:
             dist.all_reduce(best, op=dist.ReduceOp.MAX)
         with torch.cuda.device(self._device):
-            lcc = torch.empty(self._target.shape, dtype=torch.float32, device=self._device)
-            rot = torch.empty(self._target.shape, dtype=torch.int32, device=self._device)
+            lcc = torch.empty(self._shape, dtype=torch.float32, device=self._device)
+            rot = torch.empty(self._shape, dtype=torch.int32, device=self._device)
             _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
                                              self._stream()))
             self._lcc = lcc.cpu().numpy()             # powerfitter.py:536-537
@@ -255,7 +322,7 @@ class CUDACorrelator(object):
         R = rotmats.shape[0]
         with torch.cuda.device(self._device):
             g = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32)).to(self._device)
-            out = torch.empty((R,) + tuple(self._target.shape), dtype=torch.float32, device=self._device)
+            out = torch.empty((R,) + tuple(self._shape), dtype=torch.float32, device=self._device)
             _lib.check(self._libh.pfb_rotate(self._plan, g.data_ptr(), rotmats.ctypes.data_as(ctypes.c_void_p),
                                              R, int(bool(nearest)), out.data_ptr(), self._stream()))
             return out.cpu().numpy()
@@ -264,7 +331,7 @@ class CUDACorrelator(object):
         """In-place-style 3-D complex DFT, kernel exp(+2 pi i k r / n), un-normalised."""
         torch = self._torch
         v = np.ascontiguousarray(vols, dtype=np.complex64)
-        nvol = v.size // self._target.size
+        nvol = v.size // int(np.prod(self._shape))
         with torch.cuda.device(self._device):
             d = torch.from_numpy(v.view(np.float32)).to(self._device)
             _lib.check(self._libh.pfb_fft3_c2c(self._plan, d.data_ptr(), nvol, self._stream()))
@@ -278,13 +345,13 @@ class CUDACorrelator(object):
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self._device)
             g, a1, a2 = up(gcc), up(ave), up(ave2)
             if best is None:
-                best = torch.empty(self._target.size, dtype=torch.int64, device=self._device)
+                best = torch.empty(int(np.prod(self._shape)), dtype=torch.int64, device=self._device)
                 _lib.check(self._libh.pfb_best_init(self._plan, best.data_ptr(), self._stream()))
             _lib.check(self._libh.pfb_lcc_take_best(self._plan, g.data_ptr(), a1.data_ptr(), a2.data_ptr(),
                                                     float(norm_factor), int(rot_index), best.data_ptr(),
                                                     self._stream()))
-            lcc = torch.empty(self._target.shape, dtype=torch.float32, device=self._device)
-            rot = torch.empty(self._target.shape, dtype=torch.int32, device=self._device)
+            lcc = torch.empty(self._shape, dtype=torch.float32, device=self._device)
+            rot = torch.empty(self._shape, dtype=torch.int32, device=self._device)
             _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
                                              self._stream()))
             return lcc.cpu().numpy(), rot.cpu().numpy(), best

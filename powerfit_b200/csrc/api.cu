@@ -274,6 +274,31 @@ int pfb_set_template(pfb_plan *h, const float *tmpl, const float *mask, float no
     return PFB_OK;
 }
 
+int pfb_prepare_target(pfb_plan *h, const double *target, int laplace, float *f_out, uint8_t *lcc_mask_out,
+                       void *stream) {
+    PFB_REQUIRE(h && target && f_out && lcc_mask_out, "pfb_prepare_target: NULL argument");
+    Plan *p = &h->p;
+    {
+        DeviceGuard guard(p->device);
+        int rc = prep_target(p, target, laplace, f_out, lcc_mask_out, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return pfb_set_target(h, f_out, lcc_mask_out, stream);
+}
+
+int pfb_prepare_template(pfb_plan *h, const double *tmpl, const double *mask, int laplace, float *t_out, float *m_out,
+                         double *norm_factor, int *mask_is_binary, void *stream) {
+    PFB_REQUIRE(h && tmpl && mask && t_out && m_out && norm_factor && mask_is_binary,
+                "pfb_prepare_template: NULL argument");
+    Plan *p = &h->p;
+    {
+        DeviceGuard guard(p->device);
+        int rc = prep_template(p, tmpl, mask, laplace, t_out, m_out, norm_factor, mask_is_binary, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return pfb_set_template(h, t_out, m_out, (float)*norm_factor, *mask_is_binary, stream);
+}
+
 int pfb_best_init(pfb_plan *h, int64_t *best, void *stream) {
     PFB_REQUIRE(h && best, "pfb_best_init: NULL argument");
     DeviceGuard guard(h->p.device);

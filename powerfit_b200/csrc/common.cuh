@@ -79,6 +79,11 @@ int launch_unpack(Plan *p, const int64_t *best, float *lcc, int32_t *rot, cudaSt
 int launch_merge(Plan *p, int64_t *dst, const int64_t *src, cudaStream_t s);
 int launch_target_spectra(Plan *p, const float *target, cudaStream_t s);
 
+// one-time FP64 input preparation (prep.cu)
+int prep_target(Plan *p, const double *target, int laplace, float *f_out, uint8_t *lcc_mask_out, cudaStream_t s);
+int prep_template(Plan *p, const double *tmpl, const double *mask, int laplace, float *t_out, float *m_out,
+                  double *norm_factor, int *mask_is_binary, cudaStream_t s);
+
 // fused path (fused.cu)
 bool fused_supported(int nz, int ny, int nx);
 int fused_init(Plan *p);

@@ -268,6 +268,41 @@ def test_full_size_properties_128(pfb):
     assert np.abs(c2.lcc - c.lcc).max() < 1e-4 and np.array_equal(c2.rot, c.rot)
 
 
+@pytest.mark.parametrize("shape,cw,laplace", [((32, 32, 32), False, True), ((24, 30, 28), True, True),
+                                              ((64, 64, 64), True, False), ((128, 128, 128), False, True)])
+def test_device_prep_equals_host_prep(pfb, shape, cw, laplace):
+    """pfb_prepare_target / pfb_prepare_template (FP64 kernels) against the
+    reference's numpy/scipy formulas (powerfitter.py:169-220): target, lcc_mask, N and the binary flag
+    bit for bit; the z-scored template to one float32 ulp (the masked sums run in another order)."""
+    from powerfit_b200 import synth
+    case = synth.make_case(shape=shape, voxelspacing=3.0, resolution=9.0, n_res=60, rg=8.0, n_copies=2,
+                           seed=31, core_weighted=cw)
+    rots = synth.random_rotations(6, seed=2)
+    res = {}
+    for prep in ("host", "device"):
+        c = pfb.CUDACorrelator(case.target, laplace=laplace, prep=prep)
+        c.template, c.mask, c.rotations = case.template, case.mask, rots
+        c.scan()
+        res[prep] = (c._d_target.cpu().numpy(), c._lcc_mask.copy(), c._d_template.cpu().numpy(),
+                     c._d_mask.cpu().numpy(), int(c._norm_factor), c._mask_binary, c.lcc.copy(), c.rot.copy())
+    h, d = res["host"], res["device"]
+    assert np.array_equal(h[0], d[0]) and np.array_equal(h[1], d[1])
+    assert np.array_equal(h[3], d[3]) and h[4] == d[4] and h[5] == d[5] == (not cw)
+    same = h[2] == d[2]
+    assert same.mean() > 0.9999, same.mean()
+    assert np.all(np.abs(h[2] - d[2]) <= 2.4e-7 * np.maximum(np.abs(h[2]), 1e-30))
+    assert np.abs(h[6] - d[6]).max() < 1e-6
+    assert (h[7] == d[7]).mean() > 0.9999
+
+
+def test_device_prep_contract_errors(pfb):
+    t = np.random.default_rng(0).random((12, 12, 12))
+    c = pfb.CUDACorrelator(t)
+    c.template = t
+    with pytest.raises(ValueError, match="Zero-filled mask is not allowed."):
+        c.mask = np.zeros_like(t)
+
+
 def test_search_host_entry_point(pfb):
     """The all-host-buffers C-ABI call gives the same grids as the correlator."""
     import ctypes

@@ -139,3 +139,15 @@ def test_sparse_feature_maxima_equals_reference_labelling(name):
     got = set(tuple(int(c) for c in np.unravel_index(i, lcc.shape)) for i in lin)
     assert got == positions
     assert idx.size < 0.2 * lcc.size
+
+
+def test_laplace_operation_order_is_scipys():
+    """prep.cu evaluates scipy.ndimage.laplace(mode='wrap') as (d2_z + d2_y) + d2_x with
+    d2 = (-2 x[i]) + (x[i-1] + x[i+1]); this pins that order bit for bit against scipy
+    (what BaseCorrelator._laplace_filter calls, powerfitter.py:212-215)."""
+    from scipy.ndimage import laplace
+    rng = np.random.default_rng(5)
+    for shape in [(7, 9, 8), (16, 16, 16), (5, 6, 31)]:
+        x = rng.normal(size=shape) * 10.0 ** rng.integers(-3, 4, size=shape)
+        d2 = lambda a, ax: (-2.0 * a) + (np.roll(a, 1, ax) + np.roll(a, -1, ax))
+        assert np.array_equal((d2(x, 0) + d2(x, 1)) + d2(x, 2), laplace(x, mode="wrap"))

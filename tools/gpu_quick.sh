@@ -1,0 +1,7 @@
+#!/bin/bash
+# parity suite + headline bench line
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x "$@" 2>&1 | tail -15
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/err.txt | tee gpurun_out/bench_last.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('rot/s %.0f  e2e %.0f  frac %.3f' % (d['value'], d['e2e']['value'], d['roofline']['step_frac']), {k: round(1e3*v['ms_per_step']/d['config']['rotations_per_step_per_gpu'],2) for k,v in d['roofline']['kernels'].items()})"; tail -3 gpurun_out/err.txt
