@@ -281,6 +281,23 @@ def main():
     h2d = 4 * V * 3 + V + 72 * e2e_rps
     d2h = 8 * V
 
+    # ---------------- the user-level call: CUDACorrelator from host float64 arrays to host lcc/rot grids
+    # (plan creation, FP64 preparation on the device, search, download), timed once per preparation mode
+    api = {}
+    if rank == 0 or world > 1:
+        sub = rots[:rps]
+        for mode in ("device", "host"):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            c2 = CUDACorrelator(case.target, device=dev, laplace=w["laplace"], batch=args.batch, prep=mode)
+            c2.shard = False
+            c2.template, c2.mask, c2.rotations = case.template, case.mask, sub
+            c2.scan()
+            dt = time.perf_counter() - t0
+            api[mode] = {"seconds": dt, "rotations": int(rps), "rotations_per_s": rps / dt,
+                         "scan_seconds": c2.last_scan_seconds}
+            del c2
+
     # ---------------- per-kernel split (extra, untimed): events around every launch
     kernels = {}
     _lib.check(lib.pfb_profile(corr._plan, 1))
@@ -335,7 +352,10 @@ def main():
                             % (corr.plan_info(4) / 2 * (nf + 3) * 8 * V / 1e6)},
            "e2e": {"value": e2e_val, "unit": "rotations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "call": "pfb_search_host (host buffers in/out, includes FT(map) setup)"},
-           "gpu_launches": int(launches), "roofline": roof, "clocks": clocks}
+           "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+           "api_search": dict(api, call="CUDACorrelator(target) -> .template/.mask/.rotations -> .scan() from host "
+                                        "float64 arrays, one search of rotations_per_step_per_gpu rotations, "
+                                        "per preparation mode (device FP64 kernels / host numpy+scipy)")}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

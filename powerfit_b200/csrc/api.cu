@@ -160,16 +160,6 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
         PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 16);
         PFB_ALLOC(p->tmplq, sizeof(float4) * p->V);
-        if (const char *e = getenv("PFB_OVERLAP")) p->overlap = atoi(e) != 0;
-        if (const char *e = getenv("PFB_B_THREADS")) p->b_threads = atoi(e) == 256 ? 256 : 512;
-        if (p->overlap) {
-            PFB_ALLOC(p->B2, sizeof(float2) * p->V * 3 * npairs);
-            bool ok = cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking) == cudaSuccess;
-            for (int i = 0; i < 2 && ok; ++i)
-                ok = cudaEventCreateWithFlags(&p->evB[i], cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&p->evC[i], cudaEventDisableTiming) == cudaSuccess;
-            if (!ok) { set_error("pfb_plan_create: could not create the overlap stream/events"); return fail(PFB_ERR_CUDA); }
-        }
     }
 #undef PFB_ALLOC
     if ((rc = ensure_rot_capacity(p, 1024))) return fail(rc);
@@ -183,15 +173,10 @@ int pfb_plan_destroy(pfb_plan *h) {
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->B2, p->tmplq,
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->tmplq,
                     p->cls_twN, p->cls_twM, p->cls_twh, p->cls_fold};
     for (void *q : ptrs)
         if (q) cudaFree(q);
-    for (int i = 0; i < 2; ++i) {
-        if (p->evB[i]) cudaEventDestroy(p->evB[i]);
-        if (p->evC[i]) cudaEventDestroy(p->evC[i]);
-    }
-    if (p->s2) cudaStreamDestroy(p->s2);
     delete h;
     return PFB_OK;
 }
@@ -318,22 +303,6 @@ int pfb_scan(pfb_plan *h, const double *rotmats_host, int R, int rot_index_offse
     int rc = ensure_rot_capacity(p, R);
     if (rc) return rc;
     PFB_CUDA(cudaMemcpyAsync(p->rot_dev, rotmats_host, sizeof(double) * 9 * R, cudaMemcpyHostToDevice, s));
-    if (p->fused && p->overlap && !p->profile) {
-        // software pipeline over batches: A, B of batch k on the caller's stream, C of batch k on s2
-        int k = 0;
-        for (int first = 0; first < R; first += p->batch, ++k) {
-            const int count = std::min(p->batch, R - first);
-            float2 *buf = (k & 1) ? p->B2 : p->B;
-            if (k >= 2) PFB_CUDA(cudaStreamWaitEvent(s, p->evC[k & 1], 0));      // C(k-2) has drained buf
-            if ((rc = fused_front(p, first, count, buf, s))) return rc;
-            PFB_CUDA(cudaEventRecord(p->evB[k & 1], s));
-            PFB_CUDA(cudaStreamWaitEvent(p->s2, p->evB[k & 1], 0));
-            if ((rc = fused_back(p, first, count, rot_index_offset, best, buf, p->s2))) return rc;
-            PFB_CUDA(cudaEventRecord(p->evC[k & 1], p->s2));
-        }
-        for (int i = 0; i < std::min(k, 2); ++i) PFB_CUDA(cudaStreamWaitEvent(s, p->evC[i], 0));   // join
-        return PFB_OK;
-    }
     for (int first = 0; first < R; first += p->batch) {
         const int count = std::min(p->batch, R - first);
         rc = p->fused ? fused_batch(p, first, count, rot_index_offset, best, s)

@@ -127,13 +127,6 @@ struct Plan {
     float4 *cls_fold = nullptr;
     float2 *A = nullptr;                           // forward work: [batch/2][3][V]
     float2 *B = nullptr;                           // product / inverse work: [batch/2][3][V]
-    // fused path, overlapped mode: kernel C of batch n runs on a second stream next to kernels A and
-    // B of batch n+1 (B leaves shared-memory / issue slots idle, C is latency bound), X2 double-buffered
-    float2 *B2 = nullptr;
-    cudaStream_t s2 = nullptr;
-    cudaEvent_t evB[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr};
-    bool overlap = false;
-    int b_threads = 512;                           // kernel B CTA size (512, or 256 to leave room for C)
     double *rot_dev = nullptr;
     long rot_cap = 0;
     int64_t *best_scratch = nullptr;              // used by pfb_search_host

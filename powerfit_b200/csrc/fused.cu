@@ -178,7 +178,9 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     float2 *twh_s = twM + H;                                      // [H] W_N^k of the split radix-2 step
     const size_t slab = (size_t)N * H;                                                 // float4 per z
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tM = lane & (LM - 1), gM = lane / LM;
+    // LM = 4: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo the
+    // 128-byte bank window (P odd), instead of two neighbouring rows that would collide
+    const int tM = lane & (LM - 1), gM = LM == 4 ? (lane >> 3) + 4 * ((lane >> 2) & 1) : lane / LM;
     const int tN = lane & (LN - 1), gN = lane / LN;
     const int nzv = min(2 * rs + 1, N);
     // q -> (pair, volume, kx), pair fastest: the planes in flight at any time share their map-spectrum
@@ -506,8 +508,6 @@ template <int N> static int fused_init_n(Plan *p) {
                                       (int)smem_b<N>()));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_c<N>(1)));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c<N>(2)));
     return PFB_OK;
 }
 
@@ -621,9 +621,7 @@ static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int
         if (ppc_env > 0) ppc = ppc_env;
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
-        static const int nbuf = getenv("PFB_C_NBUF") ? atoi(getenv("PFB_C_NBUF")) : 1;
-        auto kern = nbuf == 2 ? fused_ifftx_lcc_kernel<N, 2> : fused_ifftx_lcc_kernel<N, 1>;
-        kern<<<dim3(N / 32, N, chunks), 128, smem_c<N>(nbuf == 2 ? 2 : 1), s>>>(
+        fused_ifftx_lcc_kernel<N, 1><<<dim3(N / 32, N, chunks), 128, smem_c<N>(1), s>>>(
             reinterpret_cast<const float4 *>(X2), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
             best, p->twdN);
     }
@@ -634,7 +632,6 @@ static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int
 int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
     if (p->cls) return cls_front(p, first, count, X2, s);
     if (p->nx == 64) return fused_front_n<64, 256>(p, first, count, X2, s);
-    if (p->b_threads == 256) return fused_front_n<128, 256>(p, first, count, X2, s);
     return fused_front_n<128, 512>(p, first, count, X2, s);
 }
 

@@ -39,9 +39,9 @@ template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS 
 // CTA = (z, tile of RN values of n, rotation pair); its NB RN rows are y = n + 64 j.  Gather
 // (as fused_rotate_fftx_kernel), x transform with 16 lanes per row, then per (kx, n) the
 // radix-NB fold over j with the class twiddles, stored as y pairs (g_b[n], g_b[n+1]).
-template <int N, bool CORNER, bool STREAM>
+template <int N>
 __global__ void __launch_bounds__(256, 2)
-cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ tmpl, const float *__restrict__ mask,
+cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ mask,
                        const double *__restrict__ rot, int first, int count, int nsig,
                        float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
                        unsigned nmask, int nzv) {
@@ -79,11 +79,11 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
         if (oy > -(N / 2) && ox * ox + oy * oy + oz * oz <= lim2) {
             float2 tv = make_float2(0.f, 0.f), mv = make_float2(0.f, 0.f);
             const SrcCoord ca = source_coord(Ra, ox, oy, oz);
-            tv.x = CORNER ? sample_trilinear_q(tmplq, d, ca) : sample_trilinear(tmpl, d, ca);
+            tv.x = sample_trilinear_q(tmplq, d, ca);
             mv.x = sample_nearest(mask, d, ca);
             if (have_b) {
                 const SrcCoord cb = source_coord(Rb, ox, oy, oz);
-                tv.y = CORNER ? sample_trilinear_q(tmplq, d, cb) : sample_trilinear(tmpl, d, cb);
+                tv.y = sample_trilinear_q(tmplq, d, cb);
                 mv.y = sample_nearest(mask, d, cb);
             }
             const int x = ox < 0 ? ox + N : ox;
@@ -139,9 +139,7 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
             }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float4 val = make_float4(g[0][b].x, g[1][b].x, g[0][b].y, g[1][b].y);
-                if (STREAM) __stcs(o + (size_t)kx * H + b * 32, val);
-                else o[(size_t)kx * H + b * 32] = val;
+                __stcs(o + (size_t)kx * H + b * 32, make_float4(g[0][b].x, g[1][b].x, g[0][b].y, g[1][b].y));
             }
         }
     };
@@ -496,10 +494,8 @@ template <int N> static int cls_init_n(Plan *p) {
         }
     if ((rc = upload_table(h, (void **)&p->cls_twh))) return rc;
     if ((rc = upload_table(f, (void **)&p->cls_fold))) return rc;
-    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
-    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
-    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
-    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_a_cls<N>()));
     PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_b_cls<N>()));
     PFB_CUDA(cudaFuncSetAttribute(cls_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -560,11 +556,8 @@ template <int N> static int cls_a_n(Plan *p, int first, int count, cudaStream_t 
     const int nzv = std::min(2 * p->rs + 1, N);
     const int ntl = __builtin_popcount(p->nmask);
     LaunchScope ls(p, KC_FUSED_A, s);
-    static const int mode = getenv("PFB_A_MODE") ? atoi(getenv("PFB_A_MODE")) : 3;   // bit 0: corner table, bit 1: streaming stores
-    auto kern = mode == 3 ? cls_rotate_fftx_kernel<N, true, true> : mode == 2 ? cls_rotate_fftx_kernel<N, false, true>
-              : mode == 1 ? cls_rotate_fftx_kernel<N, true, false> : cls_rotate_fftx_kernel<N, false, false>;
-    kern<<<dim3(nzv * ntl, npairs), 256, smem_a_cls<N>(), s>>>(
-        p->tmplq, p->tmpl, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->nmask, nzv);
+    cls_rotate_fftx_kernel<N><<<dim3(nzv * ntl, npairs), 256, smem_a_cls<N>(), s>>>(
+        p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->nmask, nzv);
     return PFB_OK;
 }
 
