@@ -286,17 +286,19 @@ def main():
     api = {}
     if rank == 0 or world > 1:
         sub = rots[:rps]
-        for mode in ("device", "host"):
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            c2 = CUDACorrelator(case.target, device=dev, laplace=w["laplace"], batch=args.batch, prep=mode)
-            c2.shard = False
-            c2.template, c2.mask, c2.rotations = case.template, case.mask, sub
-            c2.scan()
-            dt = time.perf_counter() - t0
-            api[mode] = {"seconds": dt, "rotations": int(rps), "rotations_per_s": rps / dt,
-                         "scan_seconds": c2.last_scan_seconds}
-            del c2
+        for rep in range(3):                     # best of three per mode (the first pays one-time CUDA set-up)
+            for mode in ("device", "host"):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                c2 = CUDACorrelator(case.target, device=dev, laplace=w["laplace"], batch=args.batch, prep=mode)
+                c2.shard = False
+                c2.template, c2.mask, c2.rotations = case.template, case.mask, sub
+                c2.scan()
+                dt = time.perf_counter() - t0
+                if mode not in api or dt < api[mode]["seconds"]:
+                    api[mode] = {"seconds": dt, "rotations": int(rps), "rotations_per_s": rps / dt,
+                                 "scan_seconds": c2.last_scan_seconds}
+                del c2
 
     # ---------------- per-kernel split (extra, untimed): events around every launch
     kernels = {}

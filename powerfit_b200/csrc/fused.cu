@@ -149,8 +149,9 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
 //            map spectrum (stored in the same pairing, Fpk[kx][ky][kz]), inverse z
 //   phase 3  rows, inverse y : split-in -> adjacent-out, straight to X2
 template <int N> struct FusedCfg;
-template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8; };
-template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8; };
+// CTAS: persistent CTAs of kernel B per SM (a 64^3 plane is 34 KB, so two fit and overlap their phases)
+template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8, CTAS = 2; };
+template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8, CTAS = 1; };
 
 // Persistent: one CTA per SM walks the (kx, volume, pair) planes q = blockIdx.x, + gridDim.x, ...
 // The row loop does phase 3 of the current plane and phase 1 of the CTA's next plane row by row
@@ -160,7 +161,7 @@ template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8,
 // fetching them into registers before the inverse transform 20 % slower (register pressure) --
 // the kernel is bound by shared-memory bandwidth, not by load latency.
 template <int N, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, FusedCfg<N>::CTAS)
 fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fpk,
                        const float4 *__restrict__ F2pk, const float2 *__restrict__ twN_g,
                        const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g, int rs,
@@ -598,7 +599,7 @@ static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t
     {
         LaunchScope ls(p, KC_FUSED_B, s);
         const int nplanes = N * 3 * npairs;
-        fused_fftyz_mul_kernel<N, BT><<<std::min(nplanes, p->sm_count), BT, smem_b<N>(), s>>>(
+        fused_fftyz_mul_kernel<N, BT><<<std::min(nplanes, p->sm_count * FusedCfg<N>::CTAS), BT, smem_b<N>(), s>>>(
             reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
             reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
             p->tw[0], p->rs, p->ymask, p->nsig, nplanes);
