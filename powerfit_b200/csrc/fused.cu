@@ -69,23 +69,20 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
     __syncthreads();
     const int xlo = max(-rs, -(N / 2 - 1)), W = rs - xlo + 1;
     const int lim2 = min(rs2, (N / 2) * (N / 2));
+    // both rotations of a position are fetched before either is blended (six gathers in flight); an odd
+    // last pair samples rotation a twice and discards the copy
+    const double *Rb2 = have_b ? Rb : Ra;
     for (int idx = threadIdx.x; idx < 32 * W; idx += THREADS) {
         const int r = idx / W, ox = idx % W + xlo;
         const int iy = y0 + r;
         const int oy = iy <= N / 2 ? iy : iy - N;
         if (ox * ox + oy * oy + oz * oz <= lim2) {
-            float2 tv = make_float2(0.f, 0.f), mv = make_float2(0.f, 0.f);
-            const SrcCoord ca = source_coord(Ra, ox, oy, oz);
-            tv.x = sample_trilinear_q(tmplq, d, ca);
-            mv.x = sample_nearest(mask, d, ca);
-            if (have_b) {
-                const SrcCoord cb = source_coord(Rb, ox, oy, oz);
-                tv.y = sample_trilinear_q(tmplq, d, cb);
-                mv.y = sample_nearest(mask, d, cb);
-            }
+            const SrcCoord ca = source_coord(Ra, ox, oy, oz), cb = source_coord(Rb2, ox, oy, oz);
+            const float ta = sample_trilinear_q(tmplq, d, ca), tb = sample_trilinear_q(tmplq, d, cb);
+            const float ma = sample_nearest(mask, d, ca), mb = sample_nearest(mask, d, cb);
             const int x = ox < 0 ? ox + N : ox;
-            tile_t[x * TP + r] = tv;
-            tile_m[x * TP + r] = mv;
+            tile_t[x * TP + r] = make_float2(ta, have_b ? tb : 0.f);
+            tile_m[x * TP + r] = make_float2(ma, have_b ? mb : 0.f);
         }
     }
     __syncthreads();
