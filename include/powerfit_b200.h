@@ -154,6 +154,25 @@ int pfb_lcc_max(const float *lcc, int64_t n, float *max_out, int32_t *scratch, v
 int pfb_peak_candidates(const float *lcc, int64_t n, float cutoff, int32_t cap, int32_t *idx, float *val,
                         int32_t *count, void *stream);
 
+/* ---- template / mask synthesis: what powerfit.py:245-267 calls before the search ---- */
+
+/* _powerfit.blur_points(points, weights, sigma, out, wraparound=True) (_powerfit.pyx:75-138):
+ * out[z,y,x] += w_n exp(-d^2 / (2 sigma^2)) for every atom n within 4 sigma, positions -n+1..n-1
+ * wrapping to index mod n.  points = 3 x n doubles (x row, y row, z row, grid units), all DEVICE;
+ * out = nz*ny*nx doubles, accumulated into.  Sums run in atom order like the reference's loop. */
+int pfb_blur_points(const double *points, const double *weights, int n, double sigma, int nz, int ny, int nx,
+                    double *out, void *stream);
+
+/* _powerfit.dilate_points(points, radii, out, wraparound=True) (_powerfit.pyx:141-206):
+ * out = 1 wherever a voxel lies within radii[n] of atom n (out is otherwise left as it is). */
+int pfb_dilate_points(const double *points, const double *radii, int n, int nz, int ny, int nx, double *out,
+                      void *stream);
+
+/* helpers.determine_core_indices(mask) (helpers.py:26-34): number of binary erosions (scipy's
+ * 6-neighbour cross, zero border) each voxel of mask > 0 survives, as doubles.  scratch = 2*nz*ny*nx + 16
+ * device bytes.  Synchronises the stream once per erosion level. */
+int pfb_core_indices(const double *mask, int nz, int ny, int nx, double *core, uint8_t *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,10 @@ What is restated, with the reference lines it follows (paths below
 ``OracleCorrelator``       ``powerfitter.py:166-393`` (BaseCorrelator + CPUCorrelator)
 ``partition_rotations``    ``powerfitter.py:95-108``
 ``combine_partials``       ``powerfitter.py:146-163``
+``blur_points``            ``_powerfit.pyx:75-138``  (next row N2; pinned by
+``dilate_points``          ``_powerfit.pyx:141-206``  tests/golden/shapes.npz)
+``determine_core_indices`` ``helpers.py:26-34``
+``structure_to_shape_like````volume.py:192-224``
 ``watershed_positions``    ``analyzer.py:80-95`` (next row N1; pinned by
 ``solution_rows``          ``analyzer.py:58-78``  tests/golden/analyzer_solutions.npz)
 =========================  ======================================================
@@ -359,3 +363,84 @@ def solution_rows(corr, rotmat, rotmat_ind, positions, voxelspacing=1, origin=(0
         zyx = [c * voxelspacing + o for c, o in zip(pos, origin[::-1])]
         rows.append([cc, fz, fz / z_sigma, zyx[2], zyx[1], zyx[0]] + list(np.ravel(rotmat[int(rotmat_ind[pos])])))
     return sorted(rows, key=lambda r: r[0], reverse=True)
+
+
+# --------------------------------------------------------------------------- #
+# next row N2: template / mask synthesis from atom coordinates
+# --------------------------------------------------------------------------- #
+def _axis_range(p, reach, n):
+    """The reference's clipped loop range along one axis (wraparound=True)."""
+    lo = max(int(np.ceil(p - reach)), -n + 1)
+    hi = min(int(np.floor(p + reach)), n - 1)
+    return np.arange(lo, hi + 1)
+
+
+def blur_points(points, weights, sigma, out, wraparound=True):
+    """_powerfit.pyx:75-138: out[z,y,x] += w_n exp(-d^2 / (2 sigma^2)) within 4 sigma, atom by atom;
+    negative positions index from the end like Python (positions -n+1 .. n-1)."""
+    assert wraparound
+    nz, ny, nx = out.shape
+    extend = 4.0 * sigma
+    extend2 = extend * extend
+    dsigma2 = 2.0 * sigma * sigma
+    for n in range(points.shape[1]):
+        xs = _axis_range(points[0, n], extend, nx)
+        ys = _axis_range(points[1, n], extend, ny)
+        zs = _axis_range(points[2, n], extend, nz)
+        if min(len(xs), len(ys), len(zs)) == 0:
+            continue
+        z2 = (zs - points[2, n]) ** 2
+        y2z2 = (ys - points[1, n])[None, :] ** 2 + z2[:, None]
+        d2 = (xs - points[0, n])[None, None, :] ** 2 + y2z2[:, :, None]
+        val = np.where(d2 <= extend2, weights[n] * np.exp(-d2 / dsigma2), 0.0)
+        # a box wider than the grid visits a voxel twice (p and p - n): add.at keeps both, in loop order
+        np.add.at(out, np.ix_(zs % nz, ys % ny, xs % nx), val)
+
+
+def dilate_points(points, radii, out, wraparound=True):
+    """_powerfit.pyx:141-206: out = 1 inside the ball of radius radii[n] around every atom."""
+    assert wraparound
+    nz, ny, nx = out.shape
+    for n in range(points.shape[1]):
+        radius = radii[n]
+        xs = _axis_range(points[0, n], radius, nx)
+        ys = _axis_range(points[1, n], radius, ny)
+        zs = _axis_range(points[2, n], radius, nz)
+        if min(len(xs), len(ys), len(zs)) == 0:
+            continue
+        z2 = (zs - points[2, n]) ** 2
+        y2z2 = (ys - points[1, n])[None, :] ** 2 + z2[:, None]
+        d2 = (xs - points[0, n])[None, None, :] ** 2 + y2z2[:, :, None]
+        np.maximum.at(out, np.ix_(zs % nz, ys % ny, xs % nx), (d2 <= radius ** 2).astype(np.float64))
+
+
+def determine_core_indices(mask):
+    """helpers.py:26-34."""
+    from scipy.ndimage import binary_erosion
+    core = np.zeros(mask.shape)
+    eroded = mask > 0
+    while eroded.sum() > 0:
+        core += eroded
+        eroded = binary_erosion(eroded)
+    return core
+
+
+def structure_to_shape_like(shape, voxelspacing, origin, xyz, resolution, weights=None, radii=None, kind="vol"):
+    """volume.py:192-224 on plain arrays: grid of `shape` with the given voxel spacing and origin."""
+    natoms = xyz.shape[1]
+    if kind == "vol" and weights is None:
+        weights = np.ones(natoms)
+    if kind == "mask":
+        if radii is None:
+            radii = np.empty(natoms, dtype=np.float64)
+            radii.fill(5)
+        radii = radii / voxelspacing
+    sigma = (resolution / (np.sqrt(2.0) * np.pi)) / voxelspacing
+    xyz_grid = xyz - np.asarray(origin, dtype=np.float64).reshape(3, 1)
+    xyz_grid = xyz_grid / voxelspacing
+    out = np.zeros(shape)
+    if kind == "vol":
+        blur_points(xyz_grid, np.asarray(weights, dtype=np.float64), sigma, out, True)
+    else:
+        dilate_points(xyz_grid, radii, out, True)
+    return out

@@ -21,7 +21,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 SYMBOLS = ["pfb_version", "pfb_last_error", "pfb_plan_create", "pfb_plan_destroy", "pfb_plan_info",
            "pfb_set_target", "pfb_set_template", "pfb_best_init", "pfb_scan", "pfb_unpack",
            "pfb_merge_best", "pfb_profile", "pfb_profile_read", "pfb_rotate", "pfb_fft3_c2c", "pfb_lcc_take_best", "pfb_search_host",
-           "pfb_lcc_max", "pfb_peak_candidates", "pfb_prepare_target", "pfb_prepare_template"]
+           "pfb_lcc_max", "pfb_peak_candidates", "pfb_prepare_target", "pfb_prepare_template",
+           "pfb_blur_points", "pfb_dilate_points", "pfb_core_indices"]
 
 _lib = None
 
@@ -88,6 +89,9 @@ def load():
     lib.pfb_search_host.argtypes = [vp, vp, vp, vp, vp, f32, i32, vp, i32, i32, vp, vp]
     lib.pfb_lcc_max.argtypes = [vp, c.c_int64, vp, vp, vp]
     lib.pfb_peak_candidates.argtypes = [vp, c.c_int64, f32, i32, vp, vp, vp, vp]
+    lib.pfb_blur_points.argtypes = [vp, vp, i32, c.c_double, i32, i32, i32, vp, vp]
+    lib.pfb_dilate_points.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.pfb_core_indices.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("pfb_version", "pfb_last_error"):

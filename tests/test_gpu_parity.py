@@ -444,3 +444,47 @@ def test_analyzer_on_device_tensor_and_search_result(pfb, oracle):
     want = np.array(oracle.solution_rows(c.lcc, rots, c.rot, pos, 2.0, (1.0, 2.0, 3.0), 0.05), dtype=np.float64)
     got = np.array(a.solutions, dtype=np.float64)
     assert np.allclose(got, want, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["small", "tiny_box", "config1"])
+def test_shapes_match_reference_golden(pfb, oracle, name):
+    """N2 on the device (pfb_blur_points, pfb_dilate_points, pfb_core_indices behind
+    powerfit_b200.shapes) against grids produced by the real reference: masks and core indices
+    exactly, densities to 1e-13 of their maximum (exp() implementations differ in the last bit)."""
+    from test_oracle import shapes_case
+    from powerfit_b200 import shapes
+    shape, vs, origin, res, xyz, weights, radii, vol, mask, mask_r, core = shapes_case(name)
+    grid = (shape, vs, origin)
+    t = shapes.structure_to_shape_like(grid, xyz, resolution=res, weights=weights, shape="vol")
+    assert t.dtype == np.float64 and t.shape == shape
+    assert np.abs(t - vol).max() <= 1e-13 * vol.max()
+    assert np.array_equal(t == 0, vol == 0)
+    m = shapes.structure_to_shape_like(grid, xyz, resolution=res, shape="mask")
+    assert np.array_equal(m, mask)
+    m2 = shapes.structure_to_shape_like(grid, xyz, resolution=res, radii=radii.copy(), shape="mask")
+    assert np.array_equal(m2, mask_r)
+    assert np.array_equal(shapes.determine_core_indices(m), core)
+    with pytest.raises(ValueError, match="weights array is of incorrect size"):
+        shapes.structure_to_shape_like(grid, xyz, resolution=res, weights=weights[:-1], shape="vol")
+
+
+def test_shapes_feed_the_search(pfb, oracle):
+    """Template and core-weighted mask synthesised on the device give the same search result as the
+    ones synthesised by the oracle's restatement of the reference code."""
+    from powerfit_b200 import shapes, synth
+    n, vs, res = 32, 3.0, 9.0
+    xyz = synth.random_walk_trace(80, 9.0, 6).T.copy()
+    w = np.full(80, 6.0)
+    case = synth.make_case(n=n, voxelspacing=vs, resolution=res, n_res=80, rg=9.0, n_copies=2, seed=6)
+    grid = ((n, n, n), vs, (0.0, 0.0, 0.0))
+    t_d = shapes.structure_to_shape_like(grid, xyz, resolution=res, weights=w, shape="vol")
+    m_d = shapes.determine_core_indices(shapes.structure_to_shape_like(grid, xyz, resolution=res, shape="mask"))
+    t_o = oracle.structure_to_shape_like((n, n, n), vs, (0, 0, 0), xyz, res, weights=w, kind="vol")
+    m_o = oracle.determine_core_indices(oracle.structure_to_shape_like((n, n, n), vs, (0, 0, 0), xyz, res, kind="mask"))
+    assert np.array_equal(m_d, m_o) and np.abs(t_d - t_o).max() <= 1e-13 * t_o.max()
+    rots = synth.random_rotations(8, seed=3)
+    res_ = []
+    for t, m in ((t_d, m_d), (t_o, m_o)):
+        c = run_scan(pfb, case.target, t, m, rots, True)
+        res_.append((c.lcc.copy(), c.rot.copy()))
+    assert np.abs(res_[0][0] - res_[1][0]).max() < 1e-6 and (res_[0][1] == res_[1][1]).mean() > 0.9999

@@ -193,3 +193,29 @@ def test_oracle_watershed_matches_reference_analyzer(oracle, name):
     assert rows.shape == solutions.shape
     assert np.array_equal(rows[:, 0], solutions[:, 0])                 # same order, same cc
     assert np.allclose(rows, solutions, rtol=0, atol=1e-12)
+
+
+SHAPE_CASES = ["small", "tiny_box", "config1"]
+
+
+def shapes_case(name):
+    g = load_golden("shapes")
+    f = lambda k: g[name + "_" + k]
+    return (tuple(int(v) for v in f("shape")), float(f("vs")), f("origin"), float(f("res")), f("xyz"), f("weights"),
+            f("radii"), f("vol"), f("mask").astype(np.float64), f("mask_radii").astype(np.float64),
+            f("core").astype(np.float64))
+
+
+@pytest.mark.parametrize("name", SHAPE_CASES)
+def test_oracle_shapes_match_reference(oracle, name):
+    """N2 restatements (blur_points, dilate_points, determine_core_indices, structure_to_shape_like)
+    against grids produced by the real reference (tests/golden/make_golden_shapes.py)."""
+    shape, vs, origin, res, xyz, weights, radii, vol, mask, mask_r, core = shapes_case(name)
+    t = oracle.structure_to_shape_like(shape, vs, origin, xyz, res, weights=weights, kind="vol")
+    assert np.abs(t - vol).max() <= 1e-13 * vol.max()
+    assert np.array_equal(t == 0, vol == 0)
+    m = oracle.structure_to_shape_like(shape, vs, origin, xyz, res, kind="mask")
+    assert np.array_equal(m, mask)
+    m2 = oracle.structure_to_shape_like(shape, vs, origin, xyz, res, radii=radii.copy(), kind="mask")
+    assert np.array_equal(m2, mask_r)
+    assert np.array_equal(oracle.determine_core_indices(m), core)
