@@ -33,7 +33,9 @@ namespace pfb {
 template <int N> struct ClsCfg;
 // LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
 // class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows)
-template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16; };
+// LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, 256 threads)
+template <> struct ClsCfg<128> { static constexpr int LN = 8, EN = 16, THREADS = 256, CTAS = 2, NB = 2, PPT = 8, LC = 8, LA = 8, RN = 16; };
+template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4; };
 
 // ------------------------------------------------------------------------------- kernel A
 // CTA = (z, tile of RN values of n, rotation pair); its NB RN rows are y = n + 64 j.  Gather
@@ -45,8 +47,9 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
                        const double *__restrict__ rot, int first, int count, int nsig,
                        float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
                        unsigned nmask, int nzv) {
-    constexpr int L = 16, E = N / L, NB = N / 64, RN = 4, ROWS = NB * RN, TP = ROWS + 1, THREADS = ROWS * L;
-    static_assert(THREADS == 256 && NB == 4, "N = 256");
+    constexpr int L = ClsCfg<N>::LA, E = N / L, NB = N / 64, RN = ClsCfg<N>::RN, ROWS = NB * RN, TP = ROWS + 1;
+    constexpr int THREADS = ROWS * L;
+    static_assert(THREADS == 256, "256 threads");
     extern __shared__ float2 smem[];
     float2 *tile_t = smem, *tile_m = smem + N * TP;
     const int pair = blockIdx.y;
@@ -95,7 +98,7 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
 
     // ---- x transforms: thread (row rr, t)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = lane & (L - 1), rr = 2 * warp + lane / L;
+    const int t = lane & (L - 1), rr = (32 / L) * warp + lane / L;
     float2 tw[E];
     load_twiddles<E>(tw, twN, t);
     float2 v[E], v2[E];
@@ -133,7 +136,12 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
             for (int e = 0; e < 2; ++e) {
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) g[e][jj] = tile[kx * TP + 2 * ps + e + RN * jj];
-                dft4(g[e][0], g[e][1], g[e][2], g[e][3]);
+                if (NB == 2) {
+                    const float2 sm = cadd(g[e][0], g[e][1]), df = csub(g[e][0], g[e][1]);
+                    g[e][0] = sm; g[e][1] = df;
+                } else {
+                    dft4(g[e][0], g[e][1], g[e][NB / 2], g[e][NB - 1]);
+                }
 #pragma unroll
                 for (int b = 1; b < NB; ++b) g[e][b] = cmulf(g[e][b], wf[e][b - 1]);
             }
@@ -238,7 +246,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) {
                         const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
-                        vn[n1] = (act && ((nmask >> (idx >> 1)) & 1u)) ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
+                        vn[n1] = (act && ((nmask >> (2 * idx / Cfg::RN)) & 1u)) ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
                     }
                     fft_row_adj2split<LM, EM>(vn, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
                     if (act) {
@@ -446,7 +454,9 @@ __global__ void cls_mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint3
 }
 
 // ------------------------------------------------------------------------------- host side
-template <int N> static constexpr size_t smem_a_cls() { return (size_t)2 * N * (4 * (N / 64) + 1) * sizeof(float2); }
+template <int N> static constexpr size_t smem_a_cls() {
+    return (size_t)2 * N * (ClsCfg<N>::RN * (N / 64) + 1) * sizeof(float2);
+}
 template <int N> static constexpr size_t smem_b_cls() {
     return (size_t)(N + 8) * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
 }
@@ -496,21 +506,34 @@ template <int N> static int cls_init_n(Plan *p) {
     if ((rc = upload_table(f, (void **)&p->cls_fold))) return rc;
     PFB_CUDA(cudaFuncSetAttribute(cls_rotate_fftx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_a_cls<N>()));
-    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_b_cls<N>()));
     PFB_CUDA(cudaFuncSetAttribute(cls_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_c_cls<N>()));
     return PFB_OK;
 }
 
-int cls_init(Plan *p) { return cls_init_n<256>(p); }
+int cls_init(Plan *p) {
+    if (p->nx == 128) {                  // kernels A and C around fused_b4.cu's kernel B
+        int rc = cls_init_n<128>(p);
+        return rc ? rc : b4_init(p);
+    }
+    int rc = cls_init_n<256>(p);
+    if (rc) return rc;
+    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b_cls<256>()));
+    return PFB_OK;
+}
 
 int cls_prepare_target(Plan *p, cudaStream_t s) {
-    const int N = p->nx, NB = N / 64, L = ClsCfg<256>::LC;
-    { LaunchScope ls(p, KC_OTHER, s);
-      cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
-    { LaunchScope ls(p, KC_OTHER, s);
-      cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N, NB); }
+    const int N = p->nx, NB = N / 64, L = N == 256 ? ClsCfg<256>::LC : ClsCfg<128>::LC;
+    if (N == 128) {
+        int rc = b4_prepare_target(p, s);
+        if (rc) return rc;
+    } else {
+        { LaunchScope ls(p, KC_OTHER, s);
+          cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
+        { LaunchScope ls(p, KC_OTHER, s);
+          cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N, NB); }
+    }
     { LaunchScope ls(p, KC_OTHER, s);
       const long rows = (long)N * N;
       cls_mask_bits_kernel<<<(unsigned)((rows * L + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, N, L, rows); }
@@ -562,16 +585,17 @@ template <int N> static int cls_a_n(Plan *p, int first, int count, cudaStream_t 
 }
 
 int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
-    int rc = cls_a_n<256>(p, first, count, s);
+    int rc = p->nx == 128 ? cls_a_n<128>(p, first, count, s) : cls_a_n<256>(p, first, count, s);
     if (rc) return rc;
-    rc = cls_b_n<256>(p, count, X2, s);
+    rc = p->nx == 128 ? b4_launch(p, count, X2, s) : cls_b_n<256>(p, count, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
 int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
-    int rc = cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
+    int rc = p->nx == 128 ? cls_c_n<128>(p, first, count, rot_index_offset, best, X2, s)
+                          : cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
