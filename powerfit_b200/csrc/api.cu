@@ -156,8 +156,6 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;
     if (p->fused) {
         p->cls = nx == 256;
-        if (const char *e = getenv("PFB_B3")) p->b3 = nx == 128 && atoi(e) != 0;
-        if (const char *e = getenv("PFB_B4")) { if (nx == 128 && atoi(e) != 0) { p->cls = true; p->b3 = false; } }
         PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
         PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 16);
@@ -196,7 +194,6 @@ int pfb_plan_info(const pfb_plan *h, int what, int64_t *value) {
         case 6: *value = p->fused ? 1 : 0; break;
         case 8: *value = p->rs; break;
         case 9: *value = p->cls ? 1 : 0; break;
-        case 10: *value = p->b3 ? 1 : 0; break;
         case 7: *value = (int64_t)(p->launches & 0x7FFFFFFF); break;
         default: set_error("pfb_plan_info: unknown field"); return PFB_ERR_INVALID;
     }

@@ -94,16 +94,6 @@ int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s);
 int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
 int launch_fused_a(Plan *p, int first, int count, cudaStream_t s);
 
-// kernel B with the plane in registers (fused_b3.cu): 128^3, PFB_B3=1
-int b3_init(Plan *p);
-int b3_prepare_target(Plan *p, cudaStream_t s);
-int b3_launch(Plan *p, int count, float2 *X2, cudaStream_t s);
-
-// kernel B on class-decimated half planes in registers (fused_b4.cu): 128^3, PFB_B4=1
-int b4_init(Plan *p);
-int b4_prepare_target(Plan *p, cudaStream_t s);
-int b4_launch(Plan *p, int count, float2 *X2, cudaStream_t s);
-
 // class-decimated fused path (fused_cls.cu): N = 256, optionally N = 128
 int cls_init(Plan *p);
 int cls_prepare_target(Plan *p, cudaStream_t s);
@@ -131,7 +121,6 @@ struct Plan {
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;
     // class-decimated variant of kernels B and C (fused_cls.cu)
-    bool b3 = false;                               // 128^3: kernel B of fused_b3.cu
     bool cls = false;
     unsigned nmask = 0;                            // tiles of 4 folded rows n (n = y mod 64) that meet the support
     float2 *cls_twN = nullptr, *cls_twM = nullptr, *cls_twh = nullptr;

@@ -513,27 +513,13 @@ bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (n
 
 int fused_init(Plan *p) {
     if (p->nx == 64) return fused_init_n<64>(p);
-    if (p->nx == 128) {
-        int rc = fused_init_n<128>(p);
-        if (!rc) rc = b3_init(p);
-        if (!rc && p->cls) rc = cls_init(p);
-        return rc;
-    }
+    if (p->nx == 128) return fused_init_n<128>(p);
     return cls_init(p);
 }
 
 int fused_prepare_target(Plan *p, cudaStream_t s) {
     if (p->cls) return cls_prepare_target(p, s);
     const int N = p->nx;
-    if (p->b3) {
-        int rc = b3_prepare_target(p, s);
-        if (rc) return rc;
-        LaunchScope ls(p, KC_OTHER, s);
-        const long rows = (long)N * N;
-        mask_bits_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, N, rows);
-        PFB_CUDA(cudaGetLastError());
-        return PFB_OK;
-    }
     dim3 grid(N / 32, N / 32, N / 2), block(32, 8);
     { LaunchScope ls(p, KC_OTHER, s);
       pair_transpose_kernel<<<grid, block, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N); }
@@ -607,11 +593,6 @@ static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t
     const int npairs = (count + 1) / 2;
     int rc = launch_fused_a(p, first, count, s);
     if (rc) return rc;
-    if (p->b3) {
-        if ((rc = b3_launch(p, count, X2, s))) return rc;
-        PFB_CUDA(cudaGetLastError());
-        return PFB_OK;
-    }
     {
         LaunchScope ls(p, KC_FUSED_B, s);
         const int nplanes = N * 3 * npairs;

@@ -34,7 +34,6 @@ template <int N> struct ClsCfg;
 // LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
 // class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows)
 // LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, 256 threads)
-template <> struct ClsCfg<128> { static constexpr int LN = 8, EN = 16, THREADS = 256, CTAS = 2, NB = 2, PPT = 8, LC = 8, LA = 8, RN = 16; };
 template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4; };
 
 // ------------------------------------------------------------------------------- kernel A
@@ -512,10 +511,6 @@ template <int N> static int cls_init_n(Plan *p) {
 }
 
 int cls_init(Plan *p) {
-    if (p->nx == 128) {                  // kernels A and C around fused_b4.cu's kernel B
-        int rc = cls_init_n<128>(p);
-        return rc ? rc : b4_init(p);
-    }
     int rc = cls_init_n<256>(p);
     if (rc) return rc;
     PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -524,16 +519,11 @@ int cls_init(Plan *p) {
 }
 
 int cls_prepare_target(Plan *p, cudaStream_t s) {
-    const int N = p->nx, NB = N / 64, L = N == 256 ? ClsCfg<256>::LC : ClsCfg<128>::LC;
-    if (N == 128) {
-        int rc = b4_prepare_target(p, s);
-        if (rc) return rc;
-    } else {
-        { LaunchScope ls(p, KC_OTHER, s);
-          cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
-        { LaunchScope ls(p, KC_OTHER, s);
-          cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N, NB); }
-    }
+    const int N = p->nx, NB = N / 64, L = ClsCfg<256>::LC;
+    { LaunchScope ls(p, KC_OTHER, s);
+      cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
+    { LaunchScope ls(p, KC_OTHER, s);
+      cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N, NB); }
     { LaunchScope ls(p, KC_OTHER, s);
       const long rows = (long)N * N;
       cls_mask_bits_kernel<<<(unsigned)((rows * L + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, N, L, rows); }
@@ -585,17 +575,16 @@ template <int N> static int cls_a_n(Plan *p, int first, int count, cudaStream_t 
 }
 
 int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
-    int rc = p->nx == 128 ? cls_a_n<128>(p, first, count, s) : cls_a_n<256>(p, first, count, s);
+    int rc = cls_a_n<256>(p, first, count, s);
     if (rc) return rc;
-    rc = p->nx == 128 ? b4_launch(p, count, X2, s) : cls_b_n<256>(p, count, X2, s);
+    rc = cls_b_n<256>(p, count, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
 int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
-    int rc = p->nx == 128 ? cls_c_n<128>(p, first, count, rot_index_offset, best, X2, s)
-                          : cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
+    int rc = cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
