@@ -170,7 +170,9 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     constexpr int NW = THREADS / 32;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                        // [N][P]
-    float4 *dummy = plane + N * P;                                // [GM][P] scratch rows of idle lanes
+    // [GM][P] scratch rows of idle pencil groups: shared by the idle groups of all warps (a benign race that
+    // racecheck reports -- nothing is read back from them into a result, see profiles/r01_sanitizer.txt)
+    float4 *dummy = plane + N * P;
     float2 *twN = reinterpret_cast<float2 *>(dummy + GM * P);     // [EN][LN] W_N^(t k1)
     float2 *twM = twN + N;                                        // [EM][LM] W_H^(t k1)
     float2 *twh_s = twM + H;                                      // [H] W_N^k of the split radix-2 step

@@ -1,13 +1,20 @@
-"""Tiny fused-path scan for compute-sanitizer (memcheck / racecheck)."""
+"""compute-sanitizer target: one small search per fused pipeline (64^3, 128^3, 256^3 class path) plus the
+device preparation and shape kernels.  Run as: compute-sanitizer --tool memcheck python tools/sanitize_scan.py"""
 import os, sys
-import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import powerfit_b200
-from powerfit_b200 import synth
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-case = synth.make_case(n=n, voxelspacing=2.0, resolution=8.0, n_res=60, rg=9.0, n_copies=2, seed=3,
-                       core_weighted=True)
-c = powerfit_b200.CUDACorrelator(case.target, laplace=False, batch=4)
-c.template, c.mask, c.rotations = case.template, case.mask, synth.random_rotations(5, seed=1)
-c.scan()
-print("fused", c.plan_info(6), "rs", c.plan_info(8), "max lcc", float(c.lcc.max()))
+import numpy as np
+from powerfit_b200 import CUDACorrelator, shapes, synth
+
+sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256]
+for n in sizes:
+    case = synth.make_case(n=n, voxelspacing=2.8, resolution=9.0, n_res=120, rg=11.0, n_copies=2, seed=3,
+                           core_weighted=(n != 128))
+    c = CUDACorrelator(case.target, laplace=True, batch=4)
+    c.template, c.mask, c.rotations = case.template, case.mask, synth.random_rotations(5, seed=2)
+    c.scan()
+    print(n, "fused", c.plan_info(6), "class", c.plan_info(9), "max lcc %.4f" % c.lcc.max(), flush=True)
+xyz = synth.random_walk_trace(40, 7.0, 1).T.copy()
+grid = ((24, 28, 20), 2.5, (0.0, 0.0, 0.0))
+t = shapes.structure_to_shape_like(grid, xyz, resolution=9.0, weights=np.full(40, 6.0), shape="vol")
+m = shapes.determine_core_indices(shapes.structure_to_shape_like(grid, xyz, resolution=9.0, shape="mask"))
+print("shapes", t.sum(), m.max(), flush=True)
