@@ -38,6 +38,8 @@ WORKLOADS = {
                     desc="synthetic 128^3 map, 10deg search, core-weighted LCC"),
     "config1": dict(n=64, laplace=False, cw=False, angle="20deg", full_R=648,
                     desc="synthetic 64^3 map @8A, 300-residue model, 20deg search (648 rot)"),
+    "config5": dict(n=192, laplace=False, cw=False, angle="2.5deg", full_R=207576,
+                    desc="synthetic 192^3 map @8A, one of 4 sub-unit templates, 2.5deg search, plain LCC (generic pipeline)"),
     "config4": dict(n=256, laplace=True, cw=True, angle="4.71deg", full_R=70728,
                     desc="ribosome-sized synthetic 256^3 map @6A, 4.71deg search, Laplace + core-weighted"),
 }
@@ -50,6 +52,8 @@ def make_inputs(workload):
         case = synth.config1(seed=0)
     elif workload == "config4":
         case = synth.config4(seed=0)
+    elif workload == "config5":
+        case = synth.config5(seed=0)
     else:
         case = synth.config2(seed=0, core_weighted=w["cw"])
     return case
@@ -201,7 +205,7 @@ def main():
     n = w["n"]
     V = n ** 3
     # one step = one full rotational search of the named angle at 128^3 (7416 rotations); bounded blocks elsewhere
-    rps = args.rot_per_step or {64: 2048, 128: w["full_R"], 256: 128}.get(n, 256)
+    rps = args.rot_per_step or {64: 2048, 128: w["full_R"], 256: 128, 192: 128}.get(n, 256)
     total_steps = args.warmup + args.steps
     rots = synth.random_rotations(rps * total_steps * world + 8, seed=1)
 

@@ -156,3 +156,9 @@ def config2(seed=0, core_weighted=False, n=128):
 def config4(seed=0, n=256):
     return make_case(n=n, voxelspacing=1.5, resolution=6.0, n_res=2500, rg=38.0, n_copies=10,
                      seed=seed, core_weighted=True, name="%d^3 6A ribosome-sized 4.71deg" % n)
+
+
+def config5(seed=0, n=192):
+    # one of the four sub-unit templates of BASELINE configs[4]: 192^3 map, plain LCC
+    return make_case(n=n, voxelspacing=2.0, resolution=8.0, n_res=1200, rg=30.0, n_copies=8,
+                     seed=seed, name="%d^3 8A sub-unit, fine search" % n)
