@@ -155,7 +155,7 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     p->fused = fused_supported(nz, ny, nx);
     if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;
     if (p->fused) {
-        p->cls = nx == 256;
+        p->cls = nx == 256 || nx == 192;
         PFB_ALLOC(p->Fq, sizeof(float2) * p->V);
         PFB_ALLOC(p->F2q, sizeof(float2) * p->V);
         PFB_ALLOC(p->mbits, sizeof(uint32_t) * (size_t)nz * ny * 16);

@@ -194,10 +194,60 @@ template <class T> __device__ __forceinline__ void dft16(T (&v)[16]) {
         for (int b = a + 1; b < 4; ++b) { const T tmp = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = tmp; }
 }
 
+__device__ __forceinline__ float2 cscale(float2 a, float f) { return make_float2(a.x * f, a.y * f); }
+__device__ __forceinline__ C2 cscale(C2 a, float f) { C2 r; r.re = pmul(a.re, pdup(f)); r.im = pmul(a.im, pdup(f)); return r; }
+__device__ __forceinline__ float2 cneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ C2 cneg(C2 a) { C2 r; r.re = pneg(a.re); r.im = pneg(a.im); return r; }
+
+// 3-point DFT, W3 = exp(+2 pi i / 3) = -1/2 + i sqrt(3)/2; results X0..X2 land in a, b, c
+template <class T> __device__ __forceinline__ void dft3(T &a, T &b, T &c) {
+    const T s = cadd(b, c), d = mul_i(cscale(csub(b, c), 0.86602540378443864676f));
+    const T m = csub(a, cscale(s, 0.5f));
+    a = cadd(a, s);
+    b = cadd(m, d);
+    c = csub(m, d);
+}
+
+// 24-point DFT, natural order in and out: n = n0 + 3 n1, k = k1 + 8 k0
+template <class T> __device__ __forceinline__ void dft24(T (&v)[24]) {
+    T t[3][8];
+#pragma unroll
+    for (int n0 = 0; n0 < 3; ++n0) {
+        T u[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) u[n1] = v[n0 + 3 * n1];
+        dft8(u);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) t[n0][k1] = u[k1];
+    }
+    // t[n0][k1] *= W24^(n0 k1)
+    t[1][1] = rotc(t[1][1], 0.96592582628906831f, 0.25881904510252074f);   // W24^1
+    t[1][2] = rotc(t[1][2], 0.86602540378443871f, 0.49999999999999994f);   // W24^2
+    t[1][3] = rot45(t[1][3]);
+    t[1][4] = rotc(t[1][4], 0.50000000000000011f, 0.8660254037844386f);   // W24^4
+    t[1][5] = rotc(t[1][5], 0.25881904510252074f, 0.96592582628906831f);   // W24^5
+    t[1][6] = mul_i(t[1][6]);
+    t[1][7] = rotc(t[1][7], -0.25881904510252063f, 0.96592582628906831f);   // W24^7
+    t[2][1] = rotc(t[2][1], 0.86602540378443871f, 0.49999999999999994f);   // W24^2
+    t[2][2] = rotc(t[2][2], 0.50000000000000011f, 0.8660254037844386f);   // W24^4
+    t[2][3] = mul_i(t[2][3]);
+    t[2][4] = rotc(t[2][4], -0.49999999999999978f, 0.86602540378443871f);   // W24^8
+    t[2][5] = rotc(t[2][5], -0.86602540378443871f, 0.49999999999999994f);   // W24^10
+    t[2][6] = cneg(t[2][6]);
+    t[2][7] = rotc(t[2][7], -0.86602540378443882f, -0.49999999999999972f);   // W24^14
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        dft3(t[0][k1], t[1][k1], t[2][k1]);
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) v[k1 + 8 * k0] = t[k0][k1];
+    }
+}
+
 template <int E, class T> struct DftReg;
 template <class T> struct DftReg<4, T> { static __device__ __forceinline__ void run(T (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); } };
 template <class T> struct DftReg<8, T> { static __device__ __forceinline__ void run(T (&v)[8]) { dft8(v); } };
 template <class T> struct DftReg<16, T> { static __device__ __forceinline__ void run(T (&v)[16]) { dft16(v); } };
+template <class T> struct DftReg<24, T> { static __device__ __forceinline__ void run(T (&v)[24]) { dft24(v); } };
 
 // ------------------------------------------------------------------ scalar pencil (L lanes x E)
 // in : v[n1] = x[t + L n1]       out: v[m] = X[t + L m]

@@ -511,7 +511,7 @@ template <int N> static int fused_init_n(Plan *p) {
     return PFB_OK;
 }
 
-bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (nx == 64 || nx == 128 || nx == 256); }
+bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (nx == 64 || nx == 128 || nx == 192 || nx == 256); }
 
 int fused_init(Plan *p) {
     if (p->nx == 64) return fused_init_n<64>(p);
@@ -565,7 +565,7 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
     unsigned nmask = 0;
     for (int y = 0; y < N; ++y) {
         const int sy = y <= N / 2 ? y : y - N;
-        if (sy >= -p->rs && sy <= p->rs) nmask |= 1u << ((y % 64) / (N == 256 ? 4 : 16));    // ClsCfg<N>::RN
+        if (sy >= -p->rs && sy <= p->rs) nmask |= 1u << ((y % 64) / (N == 256 ? 4 : 8));      // ClsCfg<N>::RN
     }
     p->nmask = nmask;
     return PFB_OK;

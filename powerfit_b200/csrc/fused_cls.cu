@@ -1,5 +1,5 @@
 // Class-decimated fused pipeline for cubic grids whose (y,z) plane does not fit one SM's shared
-// memory (N = 256).  Same three kernels as fused.cu,
+// memory (N = 192, 256).  Same three kernels as fused.cu,
 //
 //   A  cls_rotate_fftx   rotate + forward x + class fold        -> X1[pair][sig][z][kx][b][n]
 //   B  cls_fftyz_mul     forward y,z * FT(map), inverse z,y of ONE ky class
@@ -32,23 +32,24 @@ namespace pfb {
 
 template <int N> struct ClsCfg;
 // LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
-// class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows)
+// class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows); CCTAS: kernel-C CTAs per SM
 // LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, 256 threads)
-template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4; };
+template <> struct ClsCfg<192> { static constexpr int LN = 8, EN = 24, THREADS = 192, CTAS = 2, NB = 3, PPT = 4, LC = 8, LA = 8, RN = 8, CCTAS = 2; };
+template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4, CCTAS = 3; };
 
 // ------------------------------------------------------------------------------- kernel A
 // CTA = (z, tile of RN values of n, rotation pair); its NB RN rows are y = n + 64 j.  Gather
 // (as fused_rotate_fftx_kernel), x transform with 16 lanes per row, then per (kx, n) the
 // radix-NB fold over j with the class twiddles, stored as y pairs (g_b[n], g_b[n+1]).
 template <int N>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(ClsCfg<N>::NB * ClsCfg<N>::RN * ClsCfg<N>::LA, 2)
 cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ mask,
                        const double *__restrict__ rot, int first, int count, int nsig,
                        float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
                        unsigned nmask, int nzv) {
     constexpr int L = ClsCfg<N>::LA, E = N / L, NB = N / 64, RN = ClsCfg<N>::RN, ROWS = NB * RN, TP = ROWS + 1;
     constexpr int THREADS = ROWS * L;
-    static_assert(THREADS == 256, "256 threads");
+    static_assert(THREADS % 32 == 0 && THREADS % (RN / 2) == 0, "whole warps, fixed pair slot per thread");
     extern __shared__ float2 smem[];
     float2 *tile_t = smem, *tile_m = smem + N * TP;
     const int pair = blockIdx.y;
@@ -100,20 +101,12 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
     const int t = lane & (L - 1), rr = (32 / L) * warp + lane / L;
     float2 tw[E];
     load_twiddles<E>(tw, twN, t);
-    float2 v[E], v2[E];
+    float2 v[E];
 #pragma unroll
     for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
     fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
 #pragma unroll
     for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
-#pragma unroll
-    for (int n1 = 0; n1 < E; ++n1) {
-        v[n1] = tile_m[(t + L * n1) * TP + rr];
-        v2[n1] = make_float2(v[n1].x * v[n1].x, v[n1].y * v[n1].y);
-    }
-    fft_pencil<E, L>(v, tile_m + rr, TP, t, tw, true);
-#pragma unroll
-    for (int m = 0; m < E; ++m) tile_m[(t + L * m) * TP + rr] = v[m];
     __syncthreads();
 
     // ---- fold over j and store: thread (kx, pair slot ps): rows r = 2 ps, 2 ps + 1
@@ -135,12 +128,8 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
             for (int e = 0; e < 2; ++e) {
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) g[e][jj] = tile[kx * TP + 2 * ps + e + RN * jj];
-                if (NB == 2) {
-                    const float2 sm = cadd(g[e][0], g[e][1]), df = csub(g[e][0], g[e][1]);
-                    g[e][0] = sm; g[e][1] = df;
-                } else {
-                    dft4(g[e][0], g[e][1], g[e][NB / 2], g[e][NB - 1]);
-                }
+                if (NB == 3) dft3(g[e][0], g[e][1], g[e][NB - 1]);
+                else dft4(g[e][0], g[e][1], g[e][2], g[e][NB - 1]);
 #pragma unroll
                 for (int b = 1; b < NB; ++b) g[e][b] = cmulf(g[e][b], wf[e][b - 1]);
             }
@@ -151,12 +140,24 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
         }
     };
     fold_store(tile_t, 0);
+    // mask: its squares (core-weighted masks only) are parked in the template tile, which is free now
+    __syncthreads();
+#pragma unroll
+    for (int n1 = 0; n1 < E; ++n1) {
+        v[n1] = tile_m[(t + L * n1) * TP + rr];
+        if (nsig == 3) tile_t[(t + L * n1) * TP + rr] = make_float2(v[n1].x * v[n1].x, v[n1].y * v[n1].y);
+    }
+    fft_pencil<E, L>(v, tile_m + rr, TP, t, tw, true);
+#pragma unroll
+    for (int m = 0; m < E; ++m) tile_m[(t + L * m) * TP + rr] = v[m];
+    __syncthreads();
     fold_store(tile_m, 1);
     if (nsig == 3) {
-        __syncthreads();
-        fft_pencil<E, L>(v2, tile_t + rr, TP, t, tw, true);
 #pragma unroll
-        for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v2[m];
+        for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
+        fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
+#pragma unroll
+        for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
         __syncthreads();
         fold_store(tile_t, 2);
     }
@@ -293,7 +294,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 // fused_ifftx_lcc_kernel (fused.cu): ave2 kept, 1/sqrt(var) when ave arrives, LCC and the
 // running best when gcc arrives.
 template <int N>
-__global__ void __launch_bounds__(ClsCfg<N>::NB * ClsCfg<N>::PPT * ClsCfg<N>::LC, 3)
+__global__ void __launch_bounds__(ClsCfg<N>::NB * ClsCfg<N>::PPT * ClsCfg<N>::LC, ClsCfg<N>::CCTAS)
 cls_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict__ mbits,
                      const float4 *__restrict__ fold_g, float norm, int first_index, int count,
                      int pairs_per_chunk, int64_t *__restrict__ best, const float2 *__restrict__ twN_g) {
@@ -351,12 +352,8 @@ cls_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict__
             for (int bb = 0; bb < NB; ++bb) g[bb] = lds_c2(e + bb * PPT);
 #pragma unroll
             for (int bb = 1; bb < NB; ++bb) g[bb] = cmul(g[bb], twc[bb - 1]);
-            if (NB == 2) {
-                const C2 s = cadd(g[0], g[1]), d = csub(g[0], g[1]);
-                g[0] = s; g[1] = d;
-            } else {
-                dft4(g[0], g[1], g[NB / 2], g[NB - 1]);
-            }
+            if (NB == 3) dft3(g[0], g[1], g[NB - 1]);
+            else dft4(g[0], g[1], g[2], g[NB - 1]);
 #pragma unroll
             for (int bb = 0; bb < NB; ++bb) sts_c2(e + bb * PPT, g[bb]);
         }
@@ -510,16 +507,18 @@ template <int N> static int cls_init_n(Plan *p) {
     return PFB_OK;
 }
 
-int cls_init(Plan *p) {
-    int rc = cls_init_n<256>(p);
+template <int N> static int cls_init_all(Plan *p) {
+    int rc = cls_init_n<N>(p);
     if (rc) return rc;
-    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_b_cls<256>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b_cls<N>()));
     return PFB_OK;
 }
 
+int cls_init(Plan *p) { return p->nx == 192 ? cls_init_all<192>(p) : cls_init_all<256>(p); }
+
 int cls_prepare_target(Plan *p, cudaStream_t s) {
-    const int N = p->nx, NB = N / 64, L = ClsCfg<256>::LC;
+    const int N = p->nx, NB = N / 64, L = N == 192 ? ClsCfg<192>::LC : ClsCfg<256>::LC;
     { LaunchScope ls(p, KC_OTHER, s);
       cls_spectrum_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N, NB); }
     { LaunchScope ls(p, KC_OTHER, s);
@@ -552,7 +551,7 @@ template <int N> static int cls_c_n(Plan *p, int first, int count, int rot_index
     constexpr int NPC = Cfg::NB * Cfg::PPT;
     const int npairs = (count + 1) / 2;
     const int tiles = (N / 2 / NPC) * N;
-    int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * 3 + tiles - 1) / tiles));
+    int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * Cfg::CCTAS + tiles - 1) / tiles));
     int ppc = (npairs + chunks - 1) / chunks;
     static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
     if (ppc_env > 0) ppc = ppc_env;
@@ -569,22 +568,24 @@ template <int N> static int cls_a_n(Plan *p, int first, int count, cudaStream_t 
     const int nzv = std::min(2 * p->rs + 1, N);
     const int ntl = __builtin_popcount(p->nmask);
     LaunchScope ls(p, KC_FUSED_A, s);
-    cls_rotate_fftx_kernel<N><<<dim3(nzv * ntl, npairs), 256, smem_a_cls<N>(), s>>>(
+    cls_rotate_fftx_kernel<N><<<dim3(nzv * ntl, npairs), ClsCfg<N>::NB * ClsCfg<N>::RN * ClsCfg<N>::LA, smem_a_cls<N>(), s>>>(
         p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->nmask, nzv);
     return PFB_OK;
 }
 
 int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
-    int rc = cls_a_n<256>(p, first, count, s);
+    const bool n192 = p->nx == 192;
+    int rc = n192 ? cls_a_n<192>(p, first, count, s) : cls_a_n<256>(p, first, count, s);
     if (rc) return rc;
-    rc = cls_b_n<256>(p, count, X2, s);
+    rc = n192 ? cls_b_n<192>(p, count, X2, s) : cls_b_n<256>(p, count, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
 int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
-    int rc = cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
+    int rc = p->nx == 192 ? cls_c_n<192>(p, first, count, rot_index_offset, best, X2, s)
+                          : cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;

@@ -354,9 +354,10 @@ def test_fused_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace):
     assert np.array_equal(results["fused"][1], results["fused_noprune"][1])
 
 
-@pytest.mark.parametrize("n,cw,laplace,count", [(256, True, True, 5), (256, False, False, 4)])
+@pytest.mark.parametrize("n,cw,laplace,count", [(256, True, True, 5), (256, False, False, 4), (192, True, True, 5),
+                                                 (192, False, False, 6)])
 def test_class_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace, count):
-    """The class-decimated kernels (fused_cls.cu: 256^3) against the any-shape generic pipeline,
+    """The class-decimated kernels (fused_cls.cu: 192^3 and 256^3) against the any-shape generic pipeline,
     with and without support pruning, odd and even rotation counts."""
     from powerfit_b200 import synth
     case = synth.make_case(n=n, voxelspacing=2.8, resolution=9.0, n_res=200, rg=14.0,
