@@ -39,7 +39,7 @@ WORKLOADS = {
     "config1": dict(n=64, laplace=False, cw=False, angle="20deg", full_R=648,
                     desc="synthetic 64^3 map @8A, 300-residue model, 20deg search (648 rot)"),
     "config5": dict(n=192, laplace=False, cw=False, angle="2.5deg", full_R=207576,
-                    desc="synthetic 192^3 map @8A, one of 4 sub-unit templates, 2.5deg search, plain LCC (generic pipeline)"),
+                    desc="synthetic 192^3 map @8A, one of 4 sub-unit templates, 2.5deg search, plain LCC"),
     "config4": dict(n=256, laplace=True, cw=True, angle="4.71deg", full_R=70728,
                     desc="ribosome-sized synthetic 256^3 map @6A, 4.71deg search, Laplace + core-weighted"),
 }

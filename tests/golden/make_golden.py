@@ -173,6 +173,25 @@ def scan_256():
     print("scan_config4_256_subset R=%d lcc max %.4f at" % (len(rotations), lcc.max()), d["argmax"])
 
 
+def scan_192():
+    """BASELINE config 5 shape (subset): 192^3, plain LCC, 6 rotations of the 4.71 deg set + 2 true poses;
+    eight z planes of the result grids are stored."""
+    full = rotation_set(4.71)
+    idx = np.unique(np.r_[np.arange(0, len(full), len(full) // 5)[:5], len(full) - 1])
+    case = synth.config5(seed=0)
+    target, template, mask = f32(case.target), f32(case.template), f32(case.mask)
+    rotations = np.concatenate([full[idx[:3]], case.poses[1][0][None], full[idx[3:]], case.poses[5][0][None]])
+    lcc, rot, lcc2, c = run_reference_scan(target, template, mask, rotations, False)
+    planes = np.array([0, 1, 50, 96, 97, 150, 190, 191])
+    d = dict(rotations=rotations, laplace=np.array(0), planes=planes, seed=np.array(0), subset_index=idx,
+             lcc=lcc[planes].astype(np.float32), rot=rot[planes].astype(np.int32), lcc2=lcc2[planes].astype(np.float32),
+             lcc64_max=np.array(lcc.max()), argmax=np.array(np.unravel_index(np.argmax(lcc), lcc.shape)),
+             norm_factor=np.array(float(c._norm_factor)), rmax=np.array(int(c._rmax)),
+             lcc_mask=np.packbits(c._lcc_mask[planes].astype(bool)))
+    np.savez_compressed(os.path.join(HERE, "scan_config5_192_subset.npz"), **d)
+    print("scan_config5_192_subset R=%d lcc max %.4f at" % (len(rotations), lcc.max()), d["argmax"])
+
+
 def lcc_chain():
     """tests/test_powerfitter.py:67-79 -- perfect fit gives LCC 1 at index 0."""
     rng = np.random.default_rng(2)
@@ -191,8 +210,11 @@ def lcc_chain():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "256":
         scan_256()
+    elif len(sys.argv) > 1 and sys.argv[1] == "192":
+        scan_192()
     else:
         rotate_vectors()
         lcc_chain()
         scans()
         scan_256()
+        scan_192()

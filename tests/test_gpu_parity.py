@@ -384,14 +384,16 @@ def test_class_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace, count)
     assert np.array_equal(results["cls"][1], results["cls_noprune"][1])
 
 
-def test_scan_256_subset_golden(pfb):
-    """BASELINE config 4 (256^3, Laplace + core-weighted) on 6 rotations of the 4.71 degree set plus two true poses,
-    against eight z planes of the reference CPU path's result."""
+@pytest.mark.parametrize("name,maker,laplace", [("scan_config4_256_subset", "config4", True),
+                                                 ("scan_config5_192_subset", "config5", False)])
+def test_scan_class_path_subset_golden(pfb, name, maker, laplace):
+    """BASELINE configs 4 and 5 shapes (256^3 Laplace + core-weighted, 192^3 plain) on 6 rotations of the
+    4.71 degree set plus two true poses, against eight z planes of the reference CPU path's result."""
     from powerfit_b200 import synth
-    g = load_golden("scan_config4_256_subset")
-    case = synth.config4(seed=int(g["seed"]))
+    g = load_golden(name)
+    case = getattr(synth, maker)(seed=int(g["seed"]))
     f32 = lambda a: a.astype(np.float32).astype(np.float64)
-    c = run_scan(pfb, f32(case.target), f32(case.template), f32(case.mask), g["rotations"], True)
+    c = run_scan(pfb, f32(case.target), f32(case.template), f32(case.mask), g["rotations"], laplace)
     assert c.plan_info(6) == 1 and c.plan_info(9) == 1
     assert c._rmax == int(g["rmax"]) and float(c._norm_factor) == float(g["norm_factor"])
     planes = g["planes"]

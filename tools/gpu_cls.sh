@@ -1,7 +1,7 @@
 #!/bin/bash
 # class-decimated path: its parity tests, then 256^3 and 128^3 (PFB_CLS=1) bench lines
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "class_path or 256" 2>&1 | tail -15
+timeout 900 python -m pytest tests -m gpu -q -x -k "class_path" 2>&1 | tail -15
 run() { echo "== $*"; env "$@" timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline $ARGS 2>gpurun_out/err.txt | tee gpurun_out/bench_last.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('rot/s %.0f  e2e %.0f  frac %.3f' % (d['value'], d['e2e']['value'], d['roofline']['step_frac']), {k: round(1e3*v['ms_per_step']/d['config']['rotations_per_step_per_gpu'],2) for k,v in d['roofline']['kernels'].items()})"; tail -2 gpurun_out/err.txt; }
