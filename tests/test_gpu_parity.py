@@ -295,6 +295,22 @@ def test_device_prep_equals_host_prep(pfb, shape, cw, laplace):
     assert (h[7] == d[7]).mean() > 0.9999
 
 
+def test_several_templates_on_one_correlator(pfb):
+    """BASELINE configs[4] fits several sub-units into one map: re-setting template and mask on the same
+    correlator (the map spectra are kept) gives exactly what a fresh correlator gives."""
+    from powerfit_b200 import synth
+    case = synth.make_case(n=64, voxelspacing=3.0, resolution=9.0, n_res=120, rg=12.0, n_copies=3, seed=41)
+    other = synth.make_case(n=64, voxelspacing=3.0, resolution=9.0, n_res=70, rg=9.0, n_copies=1, seed=42,
+                            core_weighted=True)
+    rots = synth.random_rotations(9, seed=8)
+    shared = pfb.CUDACorrelator(case.target, laplace=True)
+    for tmpl, mask in ((case.template, case.mask), (other.template, other.mask), (case.template, case.mask)):
+        shared.template, shared.mask, shared.rotations = tmpl, mask, rots
+        shared.scan()
+        fresh = run_scan(pfb, case.target, tmpl, mask, rots, True)
+        assert np.array_equal(shared.lcc, fresh.lcc) and np.array_equal(shared.rot, fresh.rot)
+
+
 def test_device_prep_contract_errors(pfb):
     t = np.random.default_rng(0).random((12, 12, 12))
     c = pfb.CUDACorrelator(t)
