@@ -259,6 +259,22 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
         __syncthreads();
         if (q >= nplanes) break;
 
+        // pull the support rows of the CTA's next plane towards L2 while phase 2 runs (512 bytes per row and
+        // class): the row loop's direct loads then see L2 instead of HBM latency
+        {
+            const int qn = q + gridDim.x;
+            if (qn < nplanes) {
+                const int qq = qn / NB;
+                const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
+                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+                const float4 *nxt = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H + b * 32;
+                for (int i = threadIdx.x; i < 4 * nzv; i += THREADS) {
+                    const int z = ((i >> 2) - rs + N) % N;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)z * slab + 8 * (i & 3)));
+                }
+            }
+        }
+
         // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs k', k' + 32)
         {
             const int qq = q / NB;
