@@ -34,7 +34,7 @@ template <int N> struct ClsCfg;
 // LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
 // class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows); CCTAS: kernel-C CTAs per SM
 // LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, 256 threads)
-template <> struct ClsCfg<192> { static constexpr int LN = 8, EN = 24, THREADS = 192, CTAS = 2, NB = 3, PPT = 4, LC = 8, LA = 8, RN = 8, CCTAS = 2; };
+template <> struct ClsCfg<192> { static constexpr int LN = 8, EN = 24, THREADS = 128, CTAS = 2, NB = 3, PPT = 4, LC = 8, LA = 8, RN = 8, CCTAS = 2; };
 template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4, CCTAS = 3; };
 
 // ------------------------------------------------------------------------------- kernel A
