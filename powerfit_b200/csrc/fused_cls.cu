@@ -35,7 +35,7 @@ template <int N> struct ClsCfg;
 // class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows); CCTAS: kernel-C CTAs per SM
 // LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, 256 threads)
 template <> struct ClsCfg<192> { static constexpr int LN = 8, EN = 24, THREADS = 128, CTAS = 2, NB = 3, PPT = 4, LC = 8, LA = 8, RN = 8, CCTAS = 2; };
-template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 512, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4, CCTAS = 3; };
+template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 256, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4, CCTAS = 3; };
 
 // ------------------------------------------------------------------------------- kernel A
 // CTA = (z, tile of RN values of n, rotation pair); its NB RN rows are y = n + 64 j.  Gather
@@ -290,7 +290,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                     const int sz = z <= N / 2 ? z : z - N;
                     v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + c) : c2_zero();
                 }
-                if (LN >= 16) fft_pencil2_mul_late<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
+                if (LN >= 16 && THREADS > 256) fft_pencil2_mul_late<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
                 else fft_pencil2_mul<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
                 fft_pencil2<LN, EN>(v, plane + c, P, tN, tw);
 #pragma unroll
