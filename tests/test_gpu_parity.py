@@ -507,3 +507,46 @@ def test_shapes_feed_the_search(pfb, oracle):
         c = run_scan(pfb, case.target, t, m, rots, True)
         res_.append((c.lcc.copy(), c.rot.copy()))
     assert np.abs(res_[0][0] - res_[1][0]).max() < 1e-6 and (res_[0][1] == res_[1][1]).mean() > 0.9999
+
+
+NCCL_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+rank = int(sys.argv[1])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=2,
+                        device_id=torch.device("cuda", rank))
+from powerfit_b200 import CUDACorrelator
+g = np.load(os.path.join(%(root)r, "tests", "golden", "scan_32_plain.npz"))
+target, template, mask = (g[k].astype(np.float64) for k in ("target", "template", "mask"))
+c = CUDACorrelator(target, device=rank)
+c.template, c.mask, c.rotations = template, mask, g["rotations"]
+c.scan()                                   # shards the rotation list, merges with one MAX all-reduce
+ok = np.abs(c.lcc - g["lcc"]).max() <= 1e-4
+decided = (g["lcc"] - g["lcc2"]) > 1e-4
+ok = ok and np.array_equal(c.rot[decided], g["rot"][decided])
+single = CUDACorrelator(target, device=rank)
+single.shard = False
+single.template, single.mask, single.rotations = template, mask, g["rotations"]
+single.scan()
+ok = ok and np.array_equal(single.lcc, c.lcc) and np.array_equal(single.rot, c.rot)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_two_gpu_sharded_scan_equals_single_gpu(pfb, tmp_path):
+    """CUDACorrelator.scan() under a 2-rank NCCL process group: rotation blocks per rank + one packed MAX
+    all-reduce give, on every rank, exactly the single-GPU grids (and the reference golden)."""
+    import socket, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "nccl_worker.py"
+    script.write_text(NCCL_WORKER % dict(root=root, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
+    codes = [p.wait(timeout=600) for p in procs]
+    assert codes == [0, 0]
