@@ -333,10 +333,10 @@ def main():
         k = kernels[top]
         ach = alg.get(top, 0) * rps / (k["ms"] / 1e3) / 1e9
         # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch of that
-        # capture's batch, rescaled to this run's batch); null if there is no capture for this workload
+        # capture, rescaled to the rotations one launch of this run processes); null if there is no capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload][top]
-            roof["traffic"] = tr["dram_bytes_per_launch"] * corr.plan_info(4) / tr["batch"]
+            roof["traffic"] = tr["dram_bytes_per_launch"] * min(corr.plan_info(4), rps) / tr["rotations_per_launch"]
             roof["traffic_source"] = tr["source"]
         except Exception:
             pass
