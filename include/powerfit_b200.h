@@ -56,7 +56,9 @@ int pfb_plan_destroy(pfb_plan *plan);
 
 /* Query: 0 nz, 1 ny, 2 nx, 3 rmax, 4 batch, 5 device, 6 fused-path-available,
  * 7 kernel launches since plan creation (low 31 bits), 8 support radius of the template in
- * voxels (fused path), 9 class-decimated fused kernels in use (256^3; 128^3 with PFB_CLS=1). */
+ * voxels (fused path), 9 class-decimated fused kernels in use (192^3, 256^3).
+ * Environment switches read at plan creation (testing / tuning only): PFB_FUSED=0 forces the any-shape
+ * pipeline, PFB_NO_PRUNE=1 disables support pruning, PFB_BATCH=n overrides the default batch. */
 int pfb_plan_info(const pfb_plan *plan, int what, int64_t *value);
 
 /* GPUCorrelator.__init__ (powerfitter.py:410-420): takes the normalised (and, if the

@@ -1,5 +1,5 @@
 #!/bin/bash
-# class-decimated path: its parity tests, then 256^3 and 128^3 (PFB_CLS=1) bench lines
+# class-decimated path (192^3, 256^3): its parity tests, then the 256^3 and 192^3 bench lines
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x -k "class_path" 2>&1 | tail -15
 run() { echo "== $*"; env "$@" timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline $ARGS 2>gpurun_out/err.txt | tee gpurun_out/bench_last.json | python -c "
