@@ -44,6 +44,44 @@ def shard_bounds(nrot, world, rank):
     return lo, hi
 
 
+FUSED_CUBES = (64, 128, 192, 256)
+
+
+def fused_cube(shape):
+    """Edge of the smallest cubic grid with a fused pipeline that holds `shape`, or None."""
+    for n in FUSED_CUBES:
+        if max(shape) <= n:
+            return n
+    return None
+
+
+def pad_target(a, n):
+    """Zero-pad a map at the high end of every axis to n^3 (what the reference CLI's `extend` does,
+    volume.py:102-118, just further)."""
+    out = np.zeros((n, n, n), dtype=a.dtype)
+    out[:a.shape[0], :a.shape[1], :a.shape[2]] = a
+    return out
+
+
+def pad_wrapped(a, n):
+    """Zero-pad a template / mask that is centred on voxel 0 with wrap-around: non-negative offsets stay at
+    the low end of every axis, negative offsets move to the high end of the n^3 grid."""
+    out = np.zeros((n, n, n), dtype=a.dtype)
+    cuts = [s // 2 + 1 for s in a.shape]
+    for sz in (0, 1):
+        for sy in (0, 1):
+            for sx in (0, 1):
+                src, dst = [], []
+                for ax, side in enumerate((sz, sy, sx)):
+                    h, length = cuts[ax], a.shape[ax]
+                    if side == 0:
+                        src.append(slice(0, h)); dst.append(slice(0, h))
+                    else:
+                        src.append(slice(h, length)); dst.append(slice(n - (length - h), n))
+                out[tuple(dst)] = a[tuple(src)]
+    return out
+
+
 def _resolve_device(device):
     import torch
     if not torch.cuda.is_available():
@@ -65,13 +103,24 @@ def _resolve_device(device):
 class CUDACorrelator(object):
     """B200 implementation of the local cross-correlation search."""
 
-    def __init__(self, target, device=None, laplace=False, batch=0, prep="device"):
+    def __init__(self, target, device=None, laplace=False, batch=0, prep="device", pad=False):
+        """``pad=True`` (opt-in, not reference behaviour): zero-pad the map to the next cubic grid that has
+        a fused pipeline (64, 128, 192 or 256 voxels) and crop the results back.  The result is exactly
+        the search on the padded map -- what the reference computes when its own `extend` step
+        (powerfit.py:230-233) is given that size -- and about ten times faster than the any-shape pipeline;
+        near the box faces it differs from the unpadded search, whose template wraps around."""
         import torch
         self._torch = torch
         self._libh = _lib.load()
         target = np.asarray(target, dtype=np.float64)
         if target.ndim != 3:
             raise ValueError("target must be a 3-D array")
+        self._crop = None
+        if pad:
+            n = fused_cube(target.shape)
+            if n is not None and target.shape != (n, n, n):
+                self._crop = target.shape
+                target = pad_target(target, n)
         if prep not in ("device", "host"):
             raise ValueError("prep must be 'device' or 'host'")
         self._prep = prep
@@ -173,6 +222,8 @@ class CUDACorrelator(object):
     @template.setter
     def template(self, template):                      # powerfitter.py:236-243
         template = np.asarray(template)
+        if self._crop is not None and template.shape == self._crop:
+            template = pad_wrapped(template, self._shape[0])
         if template.shape != self._shape:
             raise ValueError("Shape of template does not match the target.")
         self._mask = None
@@ -188,6 +239,8 @@ class CUDACorrelator(object):
         if not self._template_set:
             raise ValueError("First set the template.")
         mask = np.asarray(mask)
+        if self._crop is not None and mask.shape == self._crop:
+            mask = pad_wrapped(mask, self._shape[0])
         if self._shape != mask.shape:
             raise ValueError("Shape of the mask is different from target.")
         torch = self._torch
@@ -303,6 +356,10 @@ class CUDACorrelator(object):
                                              self._stream()))
             self._lcc = lcc.cpu().numpy()             # powerfitter.py:536-537
             self._rot = rot.cpu().numpy()
+            if self._crop is not None:
+                nz, ny, nx = self._crop
+                self._lcc = np.ascontiguousarray(self._lcc[:nz, :ny, :nx])
+                self._rot = np.ascontiguousarray(self._rot[:nz, :ny, :nx])
         self.last_scan_seconds = time() - t0
 
     @staticmethod

@@ -33,6 +33,7 @@ class PowerFitter(object):
         self._directory = abspath('./')
         self._laplace = laplace
         self._batch = 0
+        self.pad_to_fused = False      # opt-in: see CUDACorrelator(pad=True)
 
     @property
     def directory(self):
@@ -54,7 +55,7 @@ class PowerFitter(object):
             q = self._queues[0]
             device = q if isinstance(q, (int, str)) or hasattr(q, "type") else None
         self._corr = CUDACorrelator(_array_of(self._target), device=device, laplace=self._laplace,
-                                    batch=self._batch)
+                                    batch=self._batch, pad=self.pad_to_fused)
         self._corr.template = _array_of(self._template)
         self._corr.mask = _array_of(self._mask)
         self._corr.rotations = self._rotations

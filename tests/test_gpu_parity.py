@@ -311,6 +311,26 @@ def test_several_templates_on_one_correlator(pfb):
         assert np.array_equal(shared.lcc, fresh.lcc) and np.array_equal(shared.rot, fresh.rot)
 
 
+def test_padding_to_a_fused_cube(pfb):
+    """pad=True: an arbitrary (CLI-like) shape is searched on the next fused cube; the result equals the
+    search on explicitly padded inputs exactly, and the unpadded any-shape search away from the box faces."""
+    from powerfit_b200 import synth
+    from powerfit_b200.correlator import pad_target, pad_wrapped
+    shape = (40, 50, 42)
+    case = synth.make_case(shape=shape, voxelspacing=3.0, resolution=9.0, n_res=60, rg=8.0, n_copies=2, seed=51)
+    rots = synth.random_rotations(9, seed=5)
+    c = pfb.CUDACorrelator(case.target, laplace=False, pad=True)
+    c.template, c.mask, c.rotations = case.template, case.mask, rots
+    c.scan()
+    assert c.plan_info(6) == 1 and c.lcc.shape == shape and c.rot.shape == shape
+    e = run_scan(pfb, pad_target(case.target, 64), pad_wrapped(case.template, 64), pad_wrapped(case.mask, 64), rots, False)
+    assert np.array_equal(c.lcc, e.lcc[:40, :50, :42]) and np.array_equal(c.rot, e.rot[:40, :50, :42])
+    g = run_scan(pfb, case.target, case.template, case.mask, rots, False)          # any-shape pipeline, periodic box
+    assert g.plan_info(6) == 0
+    inner = (slice(12, 28), slice(12, 38), slice(12, 30))
+    assert np.abs(c.lcc[inner] - g.lcc[inner]).max() < 1e-4
+
+
 def test_device_prep_contract_errors(pfb):
     t = np.random.default_rng(0).random((12, 12, 12))
     c = pfb.CUDACorrelator(t)

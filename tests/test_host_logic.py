@@ -151,3 +151,18 @@ def test_laplace_operation_order_is_scipys():
         x = rng.normal(size=shape) * 10.0 ** rng.integers(-3, 4, size=shape)
         d2 = lambda a, ax: (-2.0 * a) + (np.roll(a, 1, ax) + np.roll(a, -1, ax))
         assert np.array_equal((d2(x, 0) + d2(x, 1)) + d2(x, 2), laplace(x, mode="wrap"))
+
+
+def test_wrapped_padding_preserves_offsets():
+    """pad_wrapped keeps every voxel at its signed offset from voxel 0 (the template's centre)."""
+    from powerfit_b200.correlator import pad_wrapped, pad_target, fused_cube
+    rng = np.random.default_rng(3)
+    a = rng.random((10, 13, 9))
+    p = pad_wrapped(a, 64)
+    assert p.sum() == a.sum() and p.shape == (64, 64, 64)
+    for idx in [(0, 0, 0), (3, 6, 4), (9, 12, 8), (5, 7, 5), (6, 6, 4)]:
+        off = [i if i <= s // 2 else i - s for i, s in zip(idx, a.shape)]
+        assert p[tuple(o % 64 for o in off)] == a[idx]
+    t = pad_target(a, 64)
+    assert np.array_equal(t[:10, :13, :9], a) and t.sum() == a.sum()
+    assert fused_cube((40, 52, 46)) == 64 and fused_cube((100, 90, 84)) == 128 and fused_cube((300, 10, 10)) is None
