@@ -160,7 +160,7 @@ def run_reference(args, w, rank, world):
     val = n * args.steps / T
     sample = "%d rotations per step (%d per process x %d processes), oracle port of CPUCorrelator, numpy.fft FP64" % (
         n, per_core, cores)
-    out = {"impl": "reference", "metric": "rotations/s", "value": val, "unit": "rotations/s", "n_gpus": args.gpus,
+    out = {"impl": "reference", "metric": "rotations/s (LCC search)", "value": val, "unit": "rotations/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": w["desc"], "rotations_per_step": n},

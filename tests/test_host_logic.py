@@ -166,3 +166,18 @@ def test_wrapped_padding_preserves_offsets():
     t = pad_target(a, 64)
     assert np.array_equal(t[:10, :13, :9], a) and t.sum() == a.sum()
     assert fused_cube((40, 52, 46)) == 64 and fused_cube((100, 90, 84)) == 128 and fused_cube((300, 10, 10)) is None
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port of the reference CPU path on the host cores): one JSON
+    line with the keys the driver reads, same metric / unit / workload naming as the CUDA arm."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--workload", "config1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "rotations/s (LCC search)" and d["unit"] == "rotations/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "64^3" in d["config"]["workload"]
