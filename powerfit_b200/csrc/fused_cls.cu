@@ -33,13 +33,14 @@ namespace pfb {
 template <int N> struct ClsCfg;
 // LN x EN: column (z) pencils of kernel B; LC: lanes per x pencil of kernel C; PPT: y pairs per
 // class in one kernel-C tile (tile = NB * PPT pencils = 2 NB PPT rows); CCTAS: kernel-C CTAs per SM
-// LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, 256 threads)
+// LA / RN: lanes per x pencil and values of n per tile in kernel A (tile = NB * RN rows, NB * RN * LA threads);
+// THREADS / CTAS: kernel B's CTA size and CTAs per SM
 template <> struct ClsCfg<192> { static constexpr int LN = 8, EN = 24, THREADS = 128, CTAS = 2, NB = 3, PPT = 4, LC = 8, LA = 8, RN = 8, CCTAS = 2; };
 template <> struct ClsCfg<256> { static constexpr int LN = 16, EN = 16, THREADS = 256, CTAS = 1, NB = 4, PPT = 2, LC = 16, LA = 16, RN = 4, CCTAS = 3; };
 
 // ------------------------------------------------------------------------------- kernel A
 // CTA = (z, tile of RN values of n, rotation pair); its NB RN rows are y = n + 64 j.  Gather
-// (as fused_rotate_fftx_kernel), x transform with 16 lanes per row, then per (kx, n) the
+// (as fused_rotate_fftx_kernel), x transform with LA lanes per row, then per (kx, n) the
 // radix-NB fold over j with the class twiddles, stored as y pairs (g_b[n], g_b[n+1]).
 template <int N>
 __global__ void __launch_bounds__(ClsCfg<N>::NB * ClsCfg<N>::RN * ClsCfg<N>::LA, 2)
