@@ -175,6 +175,18 @@ int pfb_dilate_points(const double *points, const double *radii, int n, int nz, 
  * device bytes.  Synchronises the stream once per erosion level. */
 int pfb_core_indices(const double *mask, int nz, int ny, int nx, double *core, uint8_t *scratch, void *stream);
 
+/* ---- image pyramid: the array operations of scripts/__init__.py:93-103 ---- */
+
+/* scipy.ndimage.gaussian_filter(in, sigma, mode='constant') as volume.lower_resolution calls it
+ * (volume.py:129-141).  weights = right half of scipy's normalised kernel (radius + 1 doubles, DEVICE);
+ * tmp = scratch of the grid's size.  FP64-identical to scipy. */
+int pfb_gaussian_filter(const double *in, double *out, double *tmp, int nz, int ny, int nx, const double *weights,
+                        int radius, void *stream);
+
+/* scipy.ndimage.zoom(in, factor, order=1) as volume.resample calls it (volume.py:66-72): trilinear
+ * interpolation onto an oz*oy*ox grid, x_in = x_out (n_in - 1) / (n_out - 1). */
+int pfb_zoom_linear(const double *in, int nz, int ny, int nx, double *out, int oz, int oy, int ox, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

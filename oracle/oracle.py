@@ -29,6 +29,8 @@ What is restated, with the reference lines it follows (paths below
 ``dilate_points``          ``_powerfit.pyx:141-206``  tests/golden/shapes.npz)
 ``determine_core_indices`` ``helpers.py:26-34``
 ``structure_to_shape_like````volume.py:192-224``
+``lower_resolution``       ``volume.py:129-141`` (next row N4; pinned by
+``resample``               ``volume.py:66-72``    tests/golden/pyramid.npz)
 ``watershed_positions``    ``analyzer.py:80-95`` (next row N1; pinned by
 ``solution_rows``          ``analyzer.py:58-78``  tests/golden/analyzer_solutions.npz)
 =========================  ======================================================
@@ -444,3 +446,24 @@ def structure_to_shape_like(shape, voxelspacing, origin, xyz, resolution, weight
     else:
         dilate_points(xyz_grid, radii, out, True)
     return out
+
+
+# --------------------------------------------------------------------------- #
+# next row N4: image pyramid
+# --------------------------------------------------------------------------- #
+def lower_resolution(array, voxelspacing, res_high, res_low):
+    """volume.py:129-141."""
+    from scipy.ndimage import gaussian_filter
+    r2s = lambda r: r / (np.sqrt(2.0) * np.pi)
+    sigma_k = np.sqrt(r2s(res_low) ** 2 - r2s(res_high) ** 2) / voxelspacing
+    return gaussian_filter(array, sigma_k, mode="constant")
+
+
+def resample(array, voxelspacing, factor, order=1):
+    """volume.py:66-72."""
+    import warnings
+    from scipy.ndimage import zoom
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = zoom(array, factor, order=order)
+    return out, voxelspacing / factor

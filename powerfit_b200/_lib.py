@@ -22,7 +22,8 @@ SYMBOLS = ["pfb_version", "pfb_last_error", "pfb_plan_create", "pfb_plan_destroy
            "pfb_set_target", "pfb_set_template", "pfb_best_init", "pfb_scan", "pfb_unpack",
            "pfb_merge_best", "pfb_profile", "pfb_profile_read", "pfb_rotate", "pfb_fft3_c2c", "pfb_lcc_take_best", "pfb_search_host",
            "pfb_lcc_max", "pfb_peak_candidates", "pfb_prepare_target", "pfb_prepare_template",
-           "pfb_blur_points", "pfb_dilate_points", "pfb_core_indices"]
+           "pfb_blur_points", "pfb_dilate_points", "pfb_core_indices",
+           "pfb_gaussian_filter", "pfb_zoom_linear"]
 
 _lib = None
 
@@ -92,6 +93,8 @@ def load():
     lib.pfb_blur_points.argtypes = [vp, vp, i32, c.c_double, i32, i32, i32, vp, vp]
     lib.pfb_dilate_points.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.pfb_core_indices.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    lib.pfb_gaussian_filter.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp]
+    lib.pfb_zoom_linear.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("pfb_version", "pfb_last_error"):

@@ -570,3 +570,21 @@ def test_two_gpu_sharded_scan_equals_single_gpu(pfb, tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
     codes = [p.wait(timeout=600) for p in procs]
     assert codes == [0, 0]
+
+
+def test_pyramid_matches_reference_golden(pfb):
+    """N4 on the device (pfb_gaussian_filter, pfb_zoom_linear behind powerfit_b200.pyramid) against maps made
+    by the reference's lower_resolution / resample: the Gaussian filter bit for bit, the linear zoom to 4 ulp."""
+    from powerfit_b200 import pyramid
+    g = load_golden("pyramid")
+    vs, res0 = float(g["voxelspacing"]), float(g["resolution"])
+    levels = pyramid.image_pyramid(g["map"], vs, res0, [float(r) for r in g["targets"]], resampling_rate=2)
+    for i, res in enumerate(g["targets"]):
+        low = pyramid.lower_resolution(g["map"], vs, res0, float(res))
+        assert np.array_equal(low, g["low_%d" % i])
+        out, nvs = levels[i]
+        ref = g["res_%d" % i]
+        assert out.shape == ref.shape and nvs == float(g["vs_%d" % i])
+        assert np.abs(out - ref).max() <= 4 * np.finfo(np.float64).eps * np.abs(ref).max()
+    with pytest.raises(ValueError, match="lower than original data"):
+        pyramid.image_pyramid(g["map"], vs, res0, [4.0])

@@ -219,3 +219,14 @@ def test_oracle_shapes_match_reference(oracle, name):
     m2 = oracle.structure_to_shape_like(shape, vs, origin, xyz, res, radii=radii.copy(), kind="mask")
     assert np.array_equal(m2, mask_r)
     assert np.array_equal(oracle.determine_core_indices(m), core)
+
+
+def test_oracle_pyramid_matches_reference(oracle):
+    """N4 restatements against maps produced by the real reference (tests/golden/make_golden_pyramid.py)."""
+    g = load_golden("pyramid")
+    vs, res0 = float(g["voxelspacing"]), float(g["resolution"])
+    for i, res in enumerate(g["targets"]):
+        low = oracle.lower_resolution(g["map"], vs, res0, float(res))
+        assert np.array_equal(low, g["low_%d" % i])
+        out, nvs = oracle.resample(low, vs, vs / (float(res) / 4.0))
+        assert np.array_equal(out, g["res_%d" % i]) and nvs == float(g["vs_%d" % i])
