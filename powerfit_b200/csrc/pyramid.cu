@@ -6,7 +6,8 @@
 //                        out[i] = x[i] w[0] + sum_{j = radius..1} (x[i-j] + x[i+j]) w[j] with zeros outside the
 //                        array -- scipy's symmetric correlate1d, same order of additions, so FP64-identical
 //   pfb_zoom_linear      volume.resample (volume.py:66-72) -> scipy.ndimage.zoom(array, factor, order=1):
-//                        trilinear interpolation at x_in = x_out (n_in - 1) / (n_out - 1)
+//                        trilinear interpolation at x_in = x_out (n_in - 1) / (n_out - 1), zero where that
+//                        product exceeds n_in - 1 (scipy's mode='constant' edge behaviour, reproduced)
 //
 // in FP64 on device grids of the current device.  No plan is needed.
 #include "common.cuh"
@@ -41,6 +42,9 @@ __global__ void zoom_linear_kernel(const double *__restrict__ in, int nz, int ny
     for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long)gridDim.x * blockDim.x) {
         const int x = (int)(v % ox), y = (int)((v / ox) % oy), z = (int)(v / ((long)ox * oy));
         const double cz = z * sz, cy = y * sy, cx = x * sx;
+        // scipy's zoom runs in mode='constant': a coordinate that rounding pushes past the last sample
+        // (o * (n_in - 1)/(n_out - 1) > n_in - 1 by one ulp) counts as outside and yields 0
+        if (cz > (double)(nz - 1) || cy > (double)(ny - 1) || cx > (double)(nx - 1)) { out[v] = 0.0; continue; }
         const int z0 = min((int)floor(cz), nz - 1), y0 = min((int)floor(cy), ny - 1), x0 = min((int)floor(cx), nx - 1);
         const int z1 = min(z0 + 1, nz - 1), y1 = min(y0 + 1, ny - 1), x1 = min(x0 + 1, nx - 1);
         const double tz = cz - z0, ty = cy - y0, tx = cx - x0;
