@@ -136,7 +136,7 @@ def cpu_baseline(case, laplace, rotations, per_core=4, cores=None):
                       "(numpy.fft backend, FP64), %d processes, %.1f s" % (n, per_core, cores, dt)}
 
 
-def run_reference(args, w, rank, world):
+def run_reference(args, w, rank, world, emit):
     """--impl reference: the reference's CPU implementation (oracle port; the reference's own
     Python needs its package, which cannot travel) on this box's host cores."""
     if rank != 0:
@@ -166,7 +166,7 @@ def run_reference(args, w, rank, world):
            "config": {"workload": w["desc"], "rotations_per_step": n},
            "cpu_baseline": {"value": val, "unit": "rotations/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "rotations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -185,9 +185,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the one JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version
+    # banner there) are sent to stderr, and the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
-        run_reference(args, w, rank, world)
+        run_reference(args, w, rank, world, emit)
         return
 
     import torch
@@ -368,7 +376,7 @@ def main():
                 out["cpu_baseline"] = cpu_baseline(case, w["laplace"], rots, per_core=2 if n >= 128 else 8)
             except Exception as exc:       # the baseline must never sink the GPU number
                 out["cpu_baseline"] = {"value": None, "error": repr(exc)}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
