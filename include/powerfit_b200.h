@@ -49,7 +49,8 @@ const char *pfb_last_error(void);
 
 /* GPUCorrelator.__init__/_allocate_arrays/_build_ffts (powerfitter.py:399-460):
  * allocates every device buffer and FFT table for one (device, shape).
- * max_batch = rotations in flight per pass (rounded up to even; 0 = choose).
+ * max_batch = rotations in flight per pass (rounded up to even; 0 = choose; halved until the work buffers fit
+ * when device memory is short -- pfb_plan_info(plan, 4) reports the batch in use).
  * rmax is derived as min(nz,ny,nx)/2 (powerfitter.py:176). */
 int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan **out);
 int pfb_plan_destroy(pfb_plan *plan);

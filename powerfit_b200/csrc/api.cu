@@ -130,7 +130,6 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     }
     if (const char *e = getenv("PFB_BATCH")) max_batch = std::max(1, atoi(e));
     p->batch = (max_batch + 1) & ~1;
-    const long npairs = p->batch / 2;
     int rc = PFB_OK;
     auto fail = [&](int code) { pfb_plan_destroy(h); return code; };
     if ((rc = fft_generic_init())) return fail(rc);
@@ -150,8 +149,21 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     PFB_ALLOC(p->lcc_mask, p->V);
     PFB_ALLOC(p->F, sizeof(float2) * p->V);
     PFB_ALLOC(p->F2, sizeof(float2) * p->V);
-    PFB_ALLOC(p->A, sizeof(float2) * p->V * 3 * npairs);
-    PFB_ALLOC(p->B, sizeof(float2) * p->V * 3 * npairs);
+    // work buffers: 3 V complex per rotation pair each; if the device is short of memory (other plans, other
+    // processes) the batch is halved until they fit
+    for (;;) {
+        const size_t bytes = sizeof(float2) * (size_t)p->V * 3 * (size_t)(p->batch / 2);
+        cudaError_t ea = cudaMalloc(&p->A, bytes), eb = ea == cudaSuccess ? cudaMalloc(&p->B, bytes) : ea;
+        if (ea == cudaSuccess && eb == cudaSuccess) break;
+        if (p->A) { cudaFree(p->A); p->A = nullptr; }
+        if (p->B) { cudaFree(p->B); p->B = nullptr; }
+        cudaGetLastError();
+        if (p->batch <= 2) {
+            set_error(std::string("cudaMalloc work buffers: ") + cudaGetErrorString(ea != cudaSuccess ? ea : eb));
+            return fail(PFB_ERR_CUDA);
+        }
+        p->batch = ((p->batch / 2) + 1) & ~1;
+    }
     PFB_ALLOC(p->best_scratch, sizeof(int64_t) * p->V);
     p->fused = fused_supported(nz, ny, nx);
     if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;

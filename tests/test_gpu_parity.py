@@ -331,6 +331,18 @@ def test_padding_to_a_fused_cube(pfb):
     assert np.abs(c.lcc[inner] - g.lcc[inner]).max() < 1e-4
 
 
+def test_batch_shrinks_when_memory_is_short(pfb):
+    """A batch whose work buffers cannot be allocated is halved until they fit; results are unaffected."""
+    g = load_golden("scan_32_plain")
+    target, template, mask = golden_inputs(g, "scan_32_plain")
+    big = np.zeros((64, 64, 64))
+    big[:32, :32, :32] = target                        # 64^3 so that the request below is ~630 GB
+    c = pfb.CUDACorrelator(big, batch=100000)
+    assert 2 <= c.plan_info(4) < 100000
+    c2 = run_scan(pfb, target, template, mask, g["rotations"], False, batch=100000)
+    check_against_golden(c2, g)
+
+
 def test_device_prep_contract_errors(pfb):
     t = np.random.default_rng(0).random((12, 12, 12))
     c = pfb.CUDACorrelator(t)
