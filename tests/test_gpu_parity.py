@@ -600,3 +600,16 @@ def test_pyramid_matches_reference_golden(pfb):
         assert np.abs(out - ref).max() <= 4 * np.finfo(np.float64).eps * np.abs(ref).max()
     with pytest.raises(ValueError, match="lower than original data"):
         pyramid.image_pyramid(g["map"], vs, res0, [4.0])
+
+
+def test_target_prep_matches_reference_golden(pfb):
+    """N3: the CLI's resample -> trim -> extend sequence (powerfit.py:219-233) with the zoom on the device,
+    against the arrays the reference functions produce."""
+    from powerfit_b200 import target_prep as T
+    g = load_golden("target_prep")
+    arr, vs, origin = T.prepare_target(g["map"], float(g["voxelspacing"]), list(g["origin"]), float(g["resolution"]))
+    ref = g["final"]
+    assert arr.shape == ref.shape and vs == float(g["final_vs"]) and np.allclose(origin, g["trim_origin"], rtol=0, atol=0)
+    assert np.abs(arr - ref).max() <= 4 * np.finfo(np.float64).eps * np.abs(ref).max()
+    cube, _, _ = T.prepare_target(g["map"], float(g["voxelspacing"]), list(g["origin"]), float(g["resolution"]), fused=True)
+    assert cube.shape == (64, 64, 64) and np.array_equal(cube[:ref.shape[0], :ref.shape[1], :ref.shape[2]], arr)

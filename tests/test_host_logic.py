@@ -181,3 +181,21 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "64^3" in d["config"]["workload"]
+
+
+def test_target_prep_host_steps_match_reference():
+    """trim / extend / nearest_multiple2357 of powerfit_b200.target_prep against the reference's
+    (tests/golden/make_golden_target_prep.py); the resample step before them needs the GPU."""
+    from powerfit_b200 import target_prep as T
+    g = load_golden("target_prep")
+    assert [T.nearest_multiple2357(n) for n in range(1, 300)] == list(g["smooth"])
+    r = g["resampled"]
+    vs = float(g["final_vs"])
+    sub, origin = T.trim(r, vs, list(g["origin"]), r.max() / 10)
+    assert np.array_equal(sub, g["trimmed"]) and np.allclose(origin, g["trim_origin"], rtol=0, atol=0)
+    shape = [T.nearest_multiple2357(n) for n in sub.shape]
+    assert np.array_equal(T.extend(sub, shape), g["final"])
+    e = T.extend(sub, (16, 20, 15))
+    assert e.shape == (16, 20, 15) and np.count_nonzero(e) == np.count_nonzero(sub) and np.array_equal(e[:14, :18, :14], sub)
+    with pytest.raises(ValueError, match="Cutoff value should be lower than density max."):
+        T.trim(r, vs, [0, 0, 0], r.max())
