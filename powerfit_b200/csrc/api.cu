@@ -177,6 +177,17 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
 #undef PFB_ALLOC
     if ((rc = ensure_rot_capacity(p, 1024))) return fail(rc);
     if (p->fused && (rc = fused_init(p))) return fail(rc);
+    if (p->fused) {
+        // the side stream outranks the caller's stream: kernel A's CTAs are placed as soon as kernel C frees slots
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        if (cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("pfb_plan_create: side stream / events");
+            return fail(PFB_ERR_CUDA);
+        }
+    }
     *out = h;
     return PFB_OK;
 }
@@ -190,6 +201,9 @@ int pfb_plan_destroy(pfb_plan *h) {
                     p->cls_twN, p->cls_twM, p->cls_twh, p->cls_fold};
     for (void *q : ptrs)
         if (q) cudaFree(q);
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
+    if (p->ev_a) cudaEventDestroy(p->ev_a);
+    if (p->ev_b) cudaEventDestroy(p->ev_b);
     delete h;
     return PFB_OK;
 }
@@ -316,11 +330,10 @@ int pfb_scan(pfb_plan *h, const double *rotmats_host, int R, int rot_index_offse
     int rc = ensure_rot_capacity(p, R);
     if (rc) return rc;
     PFB_CUDA(cudaMemcpyAsync(p->rot_dev, rotmats_host, sizeof(double) * 9 * R, cudaMemcpyHostToDevice, s));
+    if (p->fused) return fused_scan(p, R, rot_index_offset, best, s);
     for (int first = 0; first < R; first += p->batch) {
         const int count = std::min(p->batch, R - first);
-        rc = p->fused ? fused_batch(p, first, count, rot_index_offset, best, s)
-                      : scan_batch_generic(p, first, count, rot_index_offset, best, s);
-        if (rc) return rc;
+        if ((rc = scan_batch_generic(p, first, count, rot_index_offset, best, s))) return rc;
     }
     return PFB_OK;
 }

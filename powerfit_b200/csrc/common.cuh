@@ -1,5 +1,6 @@
 // Shared declarations of the powerfit_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -89,16 +90,18 @@ bool fused_supported(int nz, int ny, int nx);
 int fused_init(Plan *p);
 int fused_prepare_target(Plan *p, cudaStream_t s);
 int fused_prepare_template(Plan *p, cudaStream_t s);
-int fused_batch(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s);
-int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s);
-int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
+int fused_scan(Plan *p, int R, int rot_index_offset, int64_t *best, cudaStream_t s);
+int fused_a(Plan *p, int first, int count, cudaStream_t s);
+int fused_b(Plan *p, int count, float2 *X2, cudaStream_t s);
+int fused_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
 int launch_fused_a(Plan *p, int first, int count, cudaStream_t s);
 
 // class-decimated fused path (fused_cls.cu): N = 256, optionally N = 128
 int cls_init(Plan *p);
 int cls_prepare_target(Plan *p, cudaStream_t s);
-int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s);
-int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
+int cls_a(Plan *p, int first, int count, cudaStream_t s);
+int cls_b(Plan *p, int count, float2 *X2, cudaStream_t s);
+int cls_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
 
 struct Plan {
     int nz = 0, ny = 0, nx = 0, rmax = 0, device = 0;
@@ -118,6 +121,8 @@ struct Plan {
     float2 *twdN = nullptr, *twdM = nullptr;       // packed-pencil twiddle tables [k1][t] (fft_core.cuh)
     float4 *tmplq = nullptr;                       // template corner table for kernel A's gather
     uint32_t *mbits = nullptr;                     // lcc_mask bit-packed in kernel C's lane layout
+    CUtensorMap tmapC;                             // kernel C's view of the X2 work buffer (tma.cuh)
+    const void *tmapC_base = nullptr;              // buffer the map was encoded for
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;
     // class-decimated variant of kernels B and C (fused_cls.cu)
@@ -130,6 +135,9 @@ struct Plan {
     double *rot_dev = nullptr;
     long rot_cap = 0;
     int64_t *best_scratch = nullptr;              // used by pfb_search_host
+    // side stream of the fused scan: kernel A of the next batch runs next to kernel C of the current one
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     unsigned long long launches = 0;
     int sm_count = 148;
     // per-kernel-class timing (off by default; events around every launch when on)

@@ -319,31 +319,43 @@ __device__ __forceinline__ C2 cmulw(C2 a, float2 w) {
 
 // stage 1: E-point DFTs in registers, twiddles, swizzled write to the pencil's storage
 template <int LANES, int E, class TW>
-__device__ __forceinline__ void pencil2_stage1(C2 (&v)[E], float4 *scratch, int stride, int t, const TW &tw) {
+__device__ __forceinline__ void pencil2_stage1(C2 (&v)[E], float4 *scratch, int stride, int t, const TW &tw,
+                                               bool active = true) {
     static_assert(E % LANES == 0, "E must be a multiple of LANES");
     DftReg<E, C2>::run(v);
 #pragma unroll
     for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
     __syncwarp();
+    if (active) {
 #pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) sts_c2(scratch + (k1 * LANES + (t ^ (k1 & (LANES - 1)))) * stride, v[k1]);
+        for (int k1 = 0; k1 < E; ++k1) sts_c2(scratch + (k1 * LANES + (t ^ (k1 & (LANES - 1)))) * stride, v[k1]);
+    }
     __syncwarp();
 }
 // stage 2, chunk q < E/LANES: the LANES-point DFT of k1 = t + LANES q; a[k0] = X[t + LANES (q + (E/LANES) k0)]
 template <int LANES>
-__device__ __forceinline__ void pencil2_stage2(C2 (&a)[LANES], const float4 *scratch, int stride, int t, int q) {
+__device__ __forceinline__ void pencil2_stage2(C2 (&a)[LANES], const float4 *scratch, int stride, int t, int q,
+                                               bool active = true) {
+    if (active) {
 #pragma unroll
-    for (int n0 = 0; n0 < LANES; ++n0) a[n0] = lds_c2(scratch + ((t + LANES * q) * LANES + (n0 ^ t)) * stride);
+        for (int n0 = 0; n0 < LANES; ++n0) a[n0] = lds_c2(scratch + ((t + LANES * q) * LANES + (n0 ^ t)) * stride);
+    } else {
+#pragma unroll
+        for (int n0 = 0; n0 < LANES; ++n0) a[n0] = c2_zero();
+    }
     DftReg<LANES, C2>::run(a);
 }
 
+// A pencil group without work (a row outside the support box next to rows inside it) passes active = false:
+// it takes part in the warp barriers but touches no shared memory.
 template <int LANES, int E, class TW>
-__device__ __forceinline__ void fft_pencil2(C2 (&v)[E], float4 *scratch, int stride, int t, const TW &tw) {
-    pencil2_stage1<LANES, E>(v, scratch, stride, t, tw);
+__device__ __forceinline__ void fft_pencil2(C2 (&v)[E], float4 *scratch, int stride, int t, const TW &tw,
+                                            bool active = true) {
+    pencil2_stage1<LANES, E>(v, scratch, stride, t, tw, active);
 #pragma unroll
     for (int q = 0; q < E / LANES; ++q) {
         C2 a[LANES];
-        pencil2_stage2<LANES>(a, scratch, stride, t, q);
+        pencil2_stage2<LANES>(a, scratch, stride, t, q, active);
 #pragma unroll
         for (int k0 = 0; k0 < LANES; ++k0) v[(E / LANES) * k0 + q] = a[k0];
     }
@@ -410,8 +422,8 @@ __device__ __forceinline__ void fft_pencil2_mul_late(C2 (&v)[E], float4 *scratch
 // twh[m] = W_N^(t + LANES m)
 template <int LANES, int E, class TW>
 __device__ __forceinline__ void fft_row_adj2split(C2 (&v)[E], float4 *scratch, int stride, int t,
-                                                  const TW &tw, const float2 (&twh)[E]) {
-    fft_pencil2<LANES, E>(v, scratch, stride, t, tw);
+                                                  const TW &tw, const float2 (&twh)[E], bool active = true) {
+    fft_pencil2<LANES, E>(v, scratch, stride, t, tw, active);
 #pragma unroll
     for (int m = 0; m < E; ++m) {
         const float2 o = cmulf(make_float2(v[m].re.y, v[m].im.y), twh[m]);

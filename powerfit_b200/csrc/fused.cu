@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "rotate_device.cuh"
+#include "tmem.cuh"
+#include "tma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -150,32 +152,39 @@ template <int N> struct FusedCfg;
 template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8, CTAS = 2; };
 template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8, CTAS = 1; };
 
-// Persistent: one CTA per SM walks the (kx, volume, pair) planes q = blockIdx.x, + gridDim.x, ...
-// The row loop does phase 3 of the current plane and phase 1 of the CTA's next plane row by row
-// (a row's storage is free for the next plane the moment its inverse transform has left for
-// HBM), so there are two block barriers per plane and nothing drains between planes.  Measured
-// alternatives: staging the next plane's rows in shared memory with cp.async is 4 % slower, and
-// fetching them into registers before the inverse transform 20 % slower (register pressure) --
-// the kernel is bound by shared-memory bandwidth, not by load latency.
+// Persistent: one CTA per SM walks jobs j = blockIdx.x, + gridDim.x, ...; a job is one (pair, kx) and consists
+// of the three output planes gcc, ave, ave2 in that order.  The row loop does phase 3 of the current plane and
+// phase 1 of the CTA's next plane row by row (a row's storage is free for the next plane the moment its inverse
+// transform has left for HBM), so there are two block barriers per plane and nothing drains between planes.
+// Measured alternatives: staging the next plane's rows in shared memory with cp.async is 4 % slower, and
+// fetching them into registers before the inverse transform 20 % slower (register pressure) -- the kernel is
+// bound by shared-memory bandwidth, not by load latency.
+//
+// Binary mask (nsig == 2): ave and ave2 are products of the SAME forward spectrum with FT(map) and FT(map^2).
+// The spectrum is computed once, in the ave plane; every thread parks the values it holds in tensor memory
+// (tmem.cuh) before multiplying, and the ave2 plane has no phase 1 and no forward z: its phase 2 fetches the
+// parked spectrum, multiplies by FT(map^2) and transforms back.  That removes one of three forward (y,z)
+// transforms from the shared-memory pipe.
 template <int N, int THREADS>
 __global__ void __launch_bounds__(THREADS, FusedCfg<N>::CTAS)
 fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fpk,
                        const float4 *__restrict__ F2pk, const float2 *__restrict__ twN_g,
                        const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g, int rs,
-                       unsigned ymask, int nsig, int nplanes) {
+                       unsigned ymask, int nsig, int npairs) {
     using Cfg = FusedCfg<N>;
     constexpr int H = N / 2, P = H + 1;
     constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
     constexpr int LM = Cfg::LM, EM = Cfg::EM, GM = 32 / LM;      // row pencils: packed N/2 points
     constexpr int NW = THREADS / 32;
+    constexpr uint32_t TCOLS = NW * EN;                          // TMEM columns: 4 EN per warp, 4 warps per lane quarter
+    static_assert(H / GN == NW, "one column group per warp: the TMEM stash is indexed by warp");
+    static_assert(TCOLS >= 32 && (TCOLS & (TCOLS - 1)) == 0 && TCOLS * Cfg::CTAS <= 512, "TMEM allocation");
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                        // [N][P]
-    // [GM][P] scratch rows of idle pencil groups: shared by the idle groups of all warps (a benign race that
-    // racecheck reports -- nothing is read back from them into a result, see profiles/r01_sanitizer.txt)
-    float4 *dummy = plane + N * P;
-    float2 *twN = reinterpret_cast<float2 *>(dummy + GM * P);     // [EN][LN] W_N^(t k1)
+    float2 *twN = reinterpret_cast<float2 *>(plane + N * P);      // [EN][LN] W_N^(t k1)
     float2 *twM = twN + N;                                        // [EM][LM] W_H^(t k1)
     float2 *twh_s = twM + H;                                      // [H] W_N^k of the split radix-2 step
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(twh_s + H);
     const size_t slab = (size_t)N * H;                                                 // float4 per z
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // LM = 4: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo the
@@ -183,40 +192,47 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     const int tM = lane & (LM - 1), gM = LM == 4 ? (lane >> 3) + 4 * ((lane >> 2) & 1) : lane / LM;
     const int tN = lane & (LN - 1), gN = lane / LN;
     const int nzv = min(2 * rs + 1, N);
-    // q -> (pair, volume, kx), pair fastest: the planes in flight at any time share their map-spectrum
-    // plane (kx, volume) and the two mask volumes of a pair re-read the same X1 rows back to back
-    const int npairs = nplanes / (3 * N);
+    const bool binary = nsig == 2;
+    // job -> (pair, kx), pair fastest: the jobs in flight at any time share their map-spectrum planes (kx)
+    const int njobs = npairs * N;
 
-    int q = blockIdx.x;          // plane whose phase 1 comes next
-    int qcur = -1;               // plane whose phase 2 is done (phase 3 pending)
+    int job = blockIdx.x, vol = 0;      // plane whose phase 1 comes next
+    int cjob = -1, cvol = 0;            // plane whose phase 2 is done (phase 3 pending)
     for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
     for (int i = threadIdx.x; i < H; i += THREADS) { twM[i] = twM_g[i]; twh_s[i] = twh_g[i]; }
+    if (warp == 0) tmem_alloc(tslot, TCOLS);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    // this warp's stash: lane quarter warp % 4 (the only one a warp may address), 4 EN columns
+    const uint32_t tcol = *tslot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * EN);
 
     while (true) {
-        __syncthreads();          // phase 2 of plane qcur is complete (first pass: the tables are in place)
+        __syncthreads();          // phase 2 of the current plane is complete (first pass: the tables are in place)
+        // the ave2 plane of a binary mask has no phase 1: its spectrum waits in TMEM
+        const bool fwd = job < njobs && !(binary && vol == 2);
         {
-            // ---- row loop: phase 3 of plane qcur (inverse y, shared -> HBM), then phase 1 of plane q
-            //      (forward y of the rows inside the support box, HBM -> shared)
+            // ---- row loop: phase 3 of plane (cjob, cvol) (inverse y, shared -> HBM), then phase 1 of plane
+            //      (job, vol) (forward y of the rows inside the support box, HBM -> shared)
             float2 twr[EM], twh[EM];
 #pragma unroll
             for (int m = 0; m < EM; ++m) { twr[m] = twM[m * LM + tM]; twh[m] = twh_s[tM + LM * m]; }
             const TwReg<EM> tw{twr};
             const float4 *src = X1;
-            if (q < nplanes) {
-                const int pair = q % npairs, vol = (q / npairs) % 3, kx = q / (3 * npairs);
-                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
-                src = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H;    // + z*slab + y/2
+            if (fwd) {
+                const int pair = job % npairs, kx = job / npairs;
+                src = X1 + (size_t)(pair * nsig + vol) * N * slab + (size_t)kx * H;    // + z*slab + y/2
             }
             float4 *dst = X2;
-            if (qcur >= 0) {
-                const int pair = qcur % npairs, vol = (qcur / npairs) % 3, kx = qcur / (3 * npairs);
-                dst = X2 + (size_t)(pair * 3 + vol) * N * slab + (size_t)kx * H;       // + z*slab + y/2
+            if (cjob >= 0) {
+                const int pair = cjob % npairs, kx = cjob / npairs;
+                dst = X2 + (size_t)(pair * 3 + cvol) * N * slab + (size_t)kx * H;      // + z*slab + y/2
             }
             for (int w = warp; w < N / GM; w += NW) {
                 const int z = w * GM + gM;
-                const bool act = q < nplanes && (z + rs) % N < nzv;
+                const bool act = fwd && (z + rs) % N < nzv;
                 const bool any = __any_sync(0xffffffffu, act);
-                if (qcur >= 0) {
+                if (cjob >= 0) {
                     C2 v[EM];
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) v[n1] = lds_c2(plane + z * P + tM + LM * n1);
@@ -224,16 +240,15 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 #pragma unroll
                     for (int m = 0; m < EM; ++m) stg_c2(dst + (size_t)z * slab + tM + LM * m, v[m]);
                 }
-                C2 vn[EM];                                                             // next plane's row z
                 if (any) {
+                    C2 vn[EM];                                                         // next plane's row z
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) {
                         const int jj = tM + LM * n1;                                   // y = 2jj, 2jj+1
                         vn[n1] = (act && ((ymask >> (jj >> 4)) & 1u)) ? ldg_c2(src + (size_t)z * slab + jj) : c2_zero();
                     }
-                }
-                if (any) {
-                    fft_row_adj2split<LM, EM>(vn, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
+                    // a pencil group outside the support box rides along without touching shared memory
+                    fft_row_adj2split<LM, EM>(vn, plane + z * P, 1, tM, tw, twh, act);
                     if (act) {
 #pragma unroll
                         for (int m = 0; m < EM; ++m) sts_c2(plane + z * P + tM + LM * m, vn[m]);
@@ -242,19 +257,19 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
             }
         }
         __syncthreads();
-        if (q >= nplanes) break;
+        if (job >= njobs) break;
 
-        // pull the support rows of the CTA's next plane towards L2 while phase 2 runs (one 128-byte line
-        // per thread): the row loop's direct loads then see L2 instead of HBM latency
+        // pull the support rows of the CTA's next forward plane towards L2 while phase 2 runs (one 128-byte
+        // line per thread): the row loop's direct loads then see L2 instead of HBM latency
         {
-            const int qn = q + gridDim.x;
+            int jn = job, vn = vol + 1;
+            if (vn == 3 || (binary && vn == 2)) { vn = 0; jn += gridDim.x; }
             const int nlines = nzv * 2 * __popc(ymask);
-            if (qn < nplanes && (int)threadIdx.x < nlines) {
-                const int pair = qn % npairs, vol = (qn / npairs) % 3, kx = qn / (3 * npairs);
-                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+            if (jn < njobs && (int)threadIdx.x < nlines) {
+                const int pair = jn % npairs, kx = jn / npairs;
                 const int j = threadIdx.x / (2 * __popc(ymask)), l = threadIdx.x % (2 * __popc(ymask));
                 const int z = (j - rs + N) % N, tile = __fns(ymask, 0, (l >> 1) + 1);
-                const float4 *a = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H + (size_t)z * slab +
+                const float4 *a = X1 + (size_t)(pair * nsig + vn) * N * slab + (size_t)kx * H + (size_t)z * slab +
                                   16 * tile + 8 * (l & 1);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
             }
@@ -262,27 +277,32 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 
         // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs ky, ky+H)
         {
-            const int vol = (q / npairs) % 3, kx = q / (3 * npairs);
+            const int kx = job / npairs;
             const float4 *Fm = (vol == 2 ? F2pk : Fpk) + (size_t)kx * H * N;           // + ky*N + kz
             const TwSmem<LN> tw{twN + tN};
-            for (int w = warp; w < H / GN; w += NW) {
-                const int ky = w * GN + gN;
-                C2 v[EN];
+            const int ky = warp * GN + gN;
+            C2 v[EN];
+            if (fwd) {
 #pragma unroll
                 for (int n1 = 0; n1 < EN; ++n1) {
                     const int z = tN + LN * n1;
                     const int sz = z <= N / 2 ? z : z - N;
                     v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + ky) : c2_zero();
                 }
-                fft_pencil2_mul<LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN);
-                fft_pencil2<LN, EN>(v, plane + ky, P, tN, tw);
-#pragma unroll
-                for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + ky, v[m]);
+                fft_pencil2_mul_stash<false, LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN, tcol,
+                                                     binary && vol == 1);
+                tmem_wait_st();
+            } else {
+                fft_pencil2_mul_stash<true, LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN, tcol, false);
             }
+            fft_pencil2<LN, EN>(v, plane + ky, P, tN, tw);
+#pragma unroll
+            for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + ky, v[m]);
         }
-        qcur = q;
-        q += gridDim.x;
+        cjob = job; cvol = vol;
+        if (++vol == 3) { vol = 0; job += gridDim.x; }
     }
+    if (warp == 0) tmem_dealloc(*tslot, TCOLS);
 }
 
 // ------------------------------------------------------------------------------- kernel C
@@ -417,6 +437,172 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------- kernel C, TMA-fed
+// Same work split and epilogue as above (16-row tiles, 64 threads), but the tiles arrive as 4-D tensor-map
+// boxes (tma.cuh): one elected thread arms an mbarrier and issues ONE cp.async.bulk.tensor per tile instead
+// of every thread issuing 32 16-byte cp.async copies, the copy engine keeps NBUF tiles in flight per CTA,
+// and it lays the box out in the 128-byte swizzle -- float4 (row kx, column c) at row * 8 + (c ^ (row & 7)) --
+// so the dense 128-byte rows need no padding to be conflict free.  With u = 8 t + (c ^ t) for lane t of the
+// pencil in column c, the three access patterns of the in-place pencil become
+//   load     x[t + 8 n1]                      at 64 n1 + u
+//   exchange row 8 k1 + (t ^ k), k = k1 & 7   at 64 k1 + (u ^ 9 k)
+//   gather   row 8 (t + 8 q) + (n0 ^ t)       at 512 q + 64 t + (u ^ 9 n0)
+// i.e. one XOR with an immediate per access.
+template <int N, int NBUF>
+__global__ void __launch_bounds__(64, NBUF == 1 ? 6 : (NBUF == 2 ? 4 : 3))
+fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ mbits, float norm,
+                           int first_index, int count, int pairs_per_chunk, int64_t *__restrict__ best,
+                           const float2 *__restrict__ twN_g) {
+    constexpr int RT = 16, E = N / 8, BP = N + 4, THREADS = 64, TILE = N * 8;    // TILE: float4 per tile
+    extern __shared__ uint8_t smem_raw[];
+    // the swizzle is a function of the shared-memory address: tiles start on a 1024-byte boundary
+    float4 *tile0 = reinterpret_cast<float4 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    float2 *lbest = reinterpret_cast<float2 *>(tile0 + NBUF * TILE);  // [RT][BP] (lcc, rot index bits)
+    float2 *tws = lbest + RT * BP;                                    // [E][8] W_N^(t k1)
+    uint64_t *full = reinterpret_cast<uint64_t *>(tws + N);           // [NBUF]
+    const int y0 = RT * blockIdx.x, z = blockIdx.y;
+    const int npairs = (count + 1) / 2;
+    const int p0 = blockIdx.z * pairs_per_chunk, p1 = min(npairs, p0 + pairs_per_chunk);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 7, rp = 4 * warp + (lane >> 3);              // y pair: rows y0+2rp, y0+2rp+1
+    const int u = 8 * t + (rp ^ t);
+    const size_t rowa = ((size_t)z * N + y0 + 2 * rp) * N, rowb = rowa + N;
+    float2 *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
+    const unsigned ma = mbits[((size_t)z * N + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * N + y0 + 2 * rp + 1) * 8 + t];
+    const int nitems = 3 * (p1 - p0);
+    auto issue = [&](int item) {                                      // thread 0 only
+        const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
+        uint64_t *bar = full + item % NBUF;
+        mbar_arrive_expect_tx(bar, TILE * (uint32_t)sizeof(float4));
+        tma_load_4d(tile0 + (item % NBUF) * TILE, &tmap, bar, 2 * y0, 0, z, p * 3 + vol);
+    };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) mbar_init(full + b, 1);
+        mbar_fence_init();
+        for (int i = 0; i < NBUF && i < nitems; ++i) issue(i);
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        lba[8 * m] = make_float2(0.f, 0.f);
+        lbb[8 * m] = make_float2(0.f, 0.f);
+    }
+    for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = twN_g[i];
+    __syncthreads();
+    const TwSmem<8> tw{tws + t};
+    C2 sd[E];
+    constexpr int Q = E / 8;
+    for (int item = 0; item < nitems; ++item) {
+        mbar_wait(full + item % NBUF, (uint32_t)(item / NBUF) & 1u);
+        float4 *tile = tile0 + (item % NBUF) * TILE;
+        const int p = p0 + item / 3, vi = item % 3;
+        const uint32_t ia = (uint32_t)(first_index + 2 * p);
+        const bool have_b = 2 * p + 1 < count;
+        // one straight-line body per volume kind (VI = 0 ave2, 1 ave, 2 gcc)
+        auto run_item = [&](auto vi_tag) {
+            constexpr int VI = decltype(vi_tag)::value;
+            {
+                C2 v[E];
+#pragma unroll
+                for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + 64 * n1 + u);
+                DftReg<E, C2>::run(v);
+#pragma unroll
+                for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
+                __syncwarp();
+#pragma unroll
+                for (int k1 = 0; k1 < E; ++k1) sts_c2(tile + 64 * k1 + (u ^ (9 * (k1 & 7))), v[k1]);
+                __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                // outputs x = t + 8 m, m = q + Q k0, of this chunk go straight into the epilogue
+                C2 a[8];
+#pragma unroll
+                for (int n0 = 0; n0 < 8; ++n0) a[n0] = lds_c2(tile + 512 * q + 64 * t + (u ^ (9 * n0)));
+                DftReg<8, C2>::run(a);
+                if (q == Q - 1) {
+                    __syncthreads();       // every pencil is out of the tile: hand it back to the copy engine
+                    if (threadIdx.x == 0 && item + NBUF < nitems) {
+                        fence_proxy_async_smem();
+                        issue(item + NBUF);
+                    }
+                }
+#pragma unroll
+                for (int k0 = 0; k0 < 8; ++k0) {
+                    const int m = q + Q * k0;
+                    if (VI == 0) {
+                        sd[m] = a[k0];                                     // ave2
+                    } else if (VI == 1) {                                  // 1/sqrt(N ave2 - ave^2)
+                        // var <= 0 gives inf / NaN exactly where the reference's gcc/sqrt(var) does
+                        const float2 vr = psub(pmul(sd[m].re, pdup(norm)), pmul(a[k0].re, a[k0].re));
+                        const float2 vq = psub(pmul(sd[m].im, pdup(norm)), pmul(a[k0].im, a[k0].im));
+                        sd[m].re = make_float2(rsqrtf(vr.x), rsqrtf(vr.y));
+                        sd[m].im = make_float2(rsqrtf(vq.x), rsqrtf(vq.y));
+                    } else {
+                        // (row a, row b) of rotation a / rotation b
+                        const float2 la = pmul(a[k0].re, sd[m].re), lb = pmul(a[k0].im, sd[m].im);
+                        // best of the pair first (ties and NaN: rotation a, the lower index, stays)
+                        const bool sa = have_b && (lb.x > la.x || !(la.x == la.x));
+                        const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
+                        const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
+                        const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
+                        if (((ma >> m) & 1u) && ca > lba[8 * m].x) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
+                        if (((mb >> m) & 1u) && cb > lbb[8 * m].x) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
+                    }
+                }
+            }
+        };
+        if (vi == 0) run_item(std::integral_constant<int, 0>{});
+        else if (vi == 1) run_item(std::integral_constant<int, 1>{});
+        else run_item(std::integral_constant<int, 2>{});
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        if ((ma >> m) & 1u) {
+            const float2 b = lba[8 * m];
+            if (b.x > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowa + t + 8 * m),
+                          (long long)pack_best(__float_as_uint(b.x), __float_as_uint(b.y)));
+        }
+        if ((mb >> m) & 1u) {
+            const float2 b = lbb[8 * m];
+            if (b.x > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowb + t + 8 * m),
+                          (long long)pack_best(__float_as_uint(b.x), __float_as_uint(b.y)));
+        }
+    }
+}
+
+int make_x2_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer,
+                       int box_floats, int box_kx) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available in this driver");
+            return PFB_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)row_floats, (cuuint64_t)nkx, (cuuint64_t)nz, (cuuint64_t)outer};
+    const cuuint64_t strides[3] = {(cuuint64_t)row_floats * 4, (cuuint64_t)row_floats * 4 * nkx,
+                                   (cuuint64_t)row_floats * 4 * nkx * nz};
+    const cuuint32_t box[4] = {(cuuint32_t)box_floats, (cuuint32_t)box_kx, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return PFB_ERR_CUDA;
+    }
+    return PFB_OK;
+}
+
 // ------------------------------------------------------------------------------- helpers
 // Fpk[kx][ky][kz] = (re F[kz][ky][kx], re F[kz][ky+N/2][kx], im ..., im ...), ky < N/2: the map
 // spectrum in the column pairing of kernel B's phase 2
@@ -474,12 +660,17 @@ __global__ void support_kernel(const float *__restrict__ tmpl, const float *__re
 }
 
 // ------------------------------------------------------------------------------- host side
-// plane + dummy rows + twiddle tables
+// plane + twiddle tables + the TMEM base address slot
 template <int N> static constexpr size_t smem_b() {
-    return (size_t)((N + 32 / FusedCfg<N>::LM) * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2);
+    return (size_t)(N * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2) + 16;
 }
 template <int N> static constexpr size_t smem_c(int rt) {
     return (size_t)N * (rt / 2 + 1) * sizeof(float4) + (size_t)rt * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
+}
+
+template <int N> static constexpr size_t smem_c_tma(int nbuf) {
+    return 1024 + (size_t)nbuf * N * 8 * sizeof(float4) + (size_t)16 * (N + 4) * sizeof(float2) + (size_t)N * sizeof(float2) +
+           (size_t)nbuf * sizeof(uint64_t);
 }
 
 // twiddle table of a LANES x E pencil: entry [k1][t] = exp(+2 pi i t k1 / (LANES E))
@@ -504,15 +695,16 @@ template <int N> static int fused_init_n(Plan *p) {
     constexpr int TP = 33;
     PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_b<N>()));
-    if (N >= 128)
-        PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_b<N>()));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c<N>(32)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256)>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<N>()));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_c<N>(16)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c_tma<N>(1)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c_tma<N>(2)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c_tma<N>(3)));
     return PFB_OK;
 }
 
@@ -594,20 +786,47 @@ int launch_fused_a(Plan *p, int first, int count, cudaStream_t s) {
     return fused_a_n<128, 8>(p, first, count, s);
 }
 
-// front half of a batch: A (rotate + x) and B (y, z, multiply, z, y) into the work buffer X2
+// kernel B of a batch: y, z, multiply, z, y out of X1 into the work buffer X2
 template <int N, int BT>
-static int fused_front_n(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
+static int fused_b_n(Plan *p, int count, float2 *X2, cudaStream_t s) {
     const int npairs = (count + 1) / 2;
-    int rc = launch_fused_a(p, first, count, s);
-    if (rc) return rc;
-    {
-        LaunchScope ls(p, KC_FUSED_B, s);
-        const int nplanes = N * 3 * npairs;
-        fused_fftyz_mul_kernel<N, BT><<<std::min(nplanes, p->sm_count * FusedCfg<N>::CTAS), BT, smem_b<N>(), s>>>(
-            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
-            reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
-            p->tw[0], p->rs, p->ymask, p->nsig, nplanes);
+    LaunchScope ls(p, KC_FUSED_B, s);
+    const int njobs = N * npairs;
+    fused_fftyz_mul_kernel<N, BT><<<std::min(njobs, p->sm_count * FusedCfg<N>::CTAS), BT, smem_b<N>(), s>>>(
+        reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
+        reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
+        p->tw[0], p->rs, p->ymask, p->nsig, npairs);
+    PFB_CUDA(cudaGetLastError());
+    return PFB_OK;
+}
+
+// tiles in flight per kernel-C CTA: 0 = the cp.async kernel (kept as the cross-check), 1..3 = TMA ring depth
+static int c_ring_depth() {
+    static const int v = getenv("PFB_C_TMA") ? atoi(getenv("PFB_C_TMA")) : 1;
+    return std::max(0, std::min(3, v));
+}
+
+template <int N, int NBUF>
+static int fused_back_tma(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2,
+                          cudaStream_t s) {
+    const int npairs = (count + 1) / 2;
+    if (p->tmapC_base != (const void *)X2) {
+        // X2 as [pair*3+vol][z][kx][2N floats]; box = 32 floats (8 y pairs) x all kx
+        int rc = make_x2_tensor_map(&p->tmapC, X2, 2 * N, N, N, 3L * (p->batch / 2), 32, N);
+        if (rc) return rc;
+        p->tmapC_base = X2;
     }
+    constexpr int per_sm = NBUF == 1 ? 6 : (NBUF == 2 ? 4 : 3);
+    const int tiles = (N / 16) * N;
+    // enough CTAs for ~4 waves of resident CTAs: split the pair loop into chunks
+    int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * per_sm + tiles - 1) / tiles));
+    int ppc = (npairs + chunks - 1) / chunks;
+    static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
+    if (ppc_env > 0) ppc = ppc_env;
+    chunks = (npairs + ppc - 1) / ppc;
+    LaunchScope ls(p, KC_FUSED_C, s);
+    fused_ifftx_lcc_tma_kernel<N, NBUF><<<dim3(N / 16, N, chunks), 64, smem_c_tma<N>(NBUF), s>>>(
+        p->tmapC, p->mbits, p->norm_factor, rot_index_offset + first, count, ppc, best, p->twdN);
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
@@ -617,9 +836,15 @@ template <int N>
 static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2,
                         cudaStream_t s) {
     const int npairs = (count + 1) / 2;
+    switch (c_ring_depth()) {
+        case 1: return fused_back_tma<N, 1>(p, first, count, rot_index_offset, best, X2, s);
+        case 2: return fused_back_tma<N, 2>(p, first, count, rot_index_offset, best, X2, s);
+        case 3: return fused_back_tma<N, 3>(p, first, count, rot_index_offset, best, X2, s);
+        default: break;
+    }
     {
         // enough CTAs for ~4 waves of resident CTAs: split the pair loop into chunks
-        static const int rt = getenv("PFB_C_RT") ? atoi(getenv("PFB_C_RT")) : 16;
+        const int rt = 16;
         const int tiles = (N / rt) * N, per_sm = 96 / rt;
         int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * per_sm + tiles - 1) / tiles));
         int ppc = (npairs + chunks - 1) / chunks;
@@ -627,35 +852,61 @@ static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int
         if (ppc_env > 0) ppc = ppc_env;
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
-        if (rt == 16)
-            fused_ifftx_lcc_kernel<N, 16><<<dim3(N / 16, N, chunks), 64, smem_c<N>(16), s>>>(
-                reinterpret_cast<const float4 *>(X2), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
-                best, p->twdN);
-        else
-            fused_ifftx_lcc_kernel<N, 32><<<dim3(N / 32, N, chunks), 128, smem_c<N>(32), s>>>(
-                reinterpret_cast<const float4 *>(X2), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
-                best, p->twdN);
+        fused_ifftx_lcc_kernel<N, 16><<<dim3(N / 16, N, chunks), 64, smem_c<N>(16), s>>>(
+            reinterpret_cast<const float4 *>(X2), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
+            best, p->twdN);
     }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
-int fused_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
-    if (p->cls) return cls_front(p, first, count, X2, s);
-    if (p->nx == 64) return fused_front_n<64, 256>(p, first, count, X2, s);
-    return fused_front_n<128, 512>(p, first, count, X2, s);
+int fused_a(Plan *p, int first, int count, cudaStream_t s) {
+    if (p->cls) return cls_a(p, first, count, s);
+    return launch_fused_a(p, first, count, s);
 }
 
-int fused_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
-    if (p->cls) return cls_back(p, first, count, rot_index_offset, best, X2, s);
+int fused_b(Plan *p, int count, float2 *X2, cudaStream_t s) {
+    if (p->cls) return cls_b(p, count, X2, s);
+    if (p->nx == 64) return fused_b_n<64, 256>(p, count, X2, s);
+    return fused_b_n<128, 512>(p, count, X2, s);
+}
+
+int fused_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
+    if (p->cls) return cls_c(p, first, count, rot_index_offset, best, X2, s);
     if (p->nx == 64) return fused_back_n<64>(p, first, count, rot_index_offset, best, X2, s);
     return fused_back_n<128>(p, first, count, rot_index_offset, best, X2, s);
 }
 
-int fused_batch(Plan *p, int first, int count, int rot_index_offset, int64_t *best, cudaStream_t s) {
-    int rc = fused_front(p, first, count, p->B, s);
-    if (rc) return rc;
-    return fused_back(p, first, count, rot_index_offset, best, p->B, s);
+// The whole rotation list, batch by batch.  Kernel A of batch i+1 (gather-latency bound, writes X1) runs on a
+// side stream next to kernel C of batch i (an HBM stream out of X2): A(i+1) waits for B(i), the last reader of
+// X1, and B(i+1) waits for A(i+1) and -- by stream order -- for C(i), the last reader of X2.  Per-kernel
+// profiling (events around every launch) keeps everything on one stream so that the classes do not overlap.
+int fused_scan(Plan *p, int R, int rot_index_offset, int64_t *best, cudaStream_t s) {
+    static const bool overlap_env = getenv("PFB_OVERLAP") ? atoi(getenv("PFB_OVERLAP")) != 0 : true;
+    const bool overlap = overlap_env && !p->profile && p->side != nullptr && R > p->batch;
+    int rc;
+    if (!overlap) {
+        for (int first = 0; first < R; first += p->batch) {
+            const int count = std::min(p->batch, R - first);
+            if ((rc = fused_a(p, first, count, s))) return rc;
+            if ((rc = fused_b(p, count, p->B, s))) return rc;
+            if ((rc = fused_c(p, first, count, rot_index_offset, best, p->B, s))) return rc;
+        }
+        return PFB_OK;
+    }
+    // the side stream joins after everything already queued on s (rotation upload, template set-up)
+    PFB_CUDA(cudaEventRecord(p->ev_b, s));
+    for (int first = 0; first < R; first += p->batch) {
+        const int count = std::min(p->batch, R - first);
+        PFB_CUDA(cudaStreamWaitEvent(p->side, p->ev_b, 0));
+        if ((rc = fused_a(p, first, count, p->side))) return rc;
+        PFB_CUDA(cudaEventRecord(p->ev_a, p->side));
+        PFB_CUDA(cudaStreamWaitEvent(s, p->ev_a, 0));
+        if ((rc = fused_b(p, count, p->B, s))) return rc;
+        PFB_CUDA(cudaEventRecord(p->ev_b, s));
+        if ((rc = fused_c(p, first, count, rot_index_offset, best, p->B, s))) return rc;
+    }
+    return PFB_OK;
 }
 
 }  // namespace pfb

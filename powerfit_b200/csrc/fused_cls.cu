@@ -182,8 +182,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
     constexpr int THREADS = Cfg::THREADS, NW = THREADS / 32;
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                        // [N][P]
-    float4 *dummy = plane + N * P;                                // [GM][P] scratch rows of idle lanes
-    float2 *twN = reinterpret_cast<float2 *>(dummy + GM * P);     // [EN][LN] W_N^(t k1)
+    float2 *twN = reinterpret_cast<float2 *>(plane + N * P);      // [EN][LN] W_N^(t k1)
     float2 *twM = twN + N;                                        // [EM][LM] W_32^(t k1)
     float2 *twh_s = twM + 32;                                     // [32] W_64^k of the split radix-2 step
     const size_t slab = (size_t)N * H;                            // float4 per z of X1 / X2
@@ -249,7 +248,8 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                         const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
                         vn[n1] = (act && ((nmask >> (2 * idx / Cfg::RN)) & 1u)) ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
                     }
-                    fft_row_adj2split<LM, EM>(vn, act ? plane + z * P : dummy + gM * P, 1, tM, tw, twh);
+                    // a pencil group outside the support box rides along without touching shared memory
+                    fft_row_adj2split<LM, EM>(vn, plane + z * P, 1, tM, tw, twh, act);
                     if (act) {
 #pragma unroll
                         for (int m = 0; m < EM; ++m) sts_c2(plane + z * P + tM + LM * m, vn[m]);
@@ -471,7 +471,7 @@ template <int N> static constexpr size_t smem_a_cls() {
     return (size_t)2 * N * (ClsCfg<N>::RN * (N / 64) + 1) * sizeof(float2);
 }
 template <int N> static constexpr size_t smem_b_cls() {
-    return (size_t)(N + 8) * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
+    return (size_t)N * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
 }
 template <int N> static constexpr size_t smem_c_cls() {
     using Cfg = ClsCfg<N>;
@@ -590,17 +590,21 @@ template <int N> static int cls_a_n(Plan *p, int first, int count, cudaStream_t 
     return PFB_OK;
 }
 
-int cls_front(Plan *p, int first, int count, float2 *X2, cudaStream_t s) {
-    const bool n192 = p->nx == 192;
-    int rc = n192 ? cls_a_n<192>(p, first, count, s) : cls_a_n<256>(p, first, count, s);
-    if (rc) return rc;
-    rc = n192 ? cls_b_n<192>(p, count, X2, s) : cls_b_n<256>(p, count, X2, s);
+int cls_a(Plan *p, int first, int count, cudaStream_t s) {
+    int rc = p->nx == 192 ? cls_a_n<192>(p, first, count, s) : cls_a_n<256>(p, first, count, s);
     if (rc) return rc;
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
 
-int cls_back(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
+int cls_b(Plan *p, int count, float2 *X2, cudaStream_t s) {
+    int rc = p->nx == 192 ? cls_b_n<192>(p, count, X2, s) : cls_b_n<256>(p, count, X2, s);
+    if (rc) return rc;
+    PFB_CUDA(cudaGetLastError());
+    return PFB_OK;
+}
+
+int cls_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
     int rc = p->nx == 192 ? cls_c_n<192>(p, first, count, rot_index_offset, best, X2, s)
                           : cls_c_n<256>(p, first, count, rot_index_offset, best, X2, s);
     if (rc) return rc;
