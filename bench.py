@@ -12,8 +12,12 @@ step ends with the packed MAX all-reduce that merges the ranks' grids.  `value` 
 rotations/s over all ranks with inputs resident in HBM; `e2e` is the same metric through
 the C-ABI call that takes HOST buffers (`pfb_search_host`: uploads, FT(map), search,
 unpack, downloads).  `roofline` follows SURVEY.md section 8(d): B_rot = (2 n_f + 6) S bytes per
-rotation.  `cpu_baseline` times the oracle port of the reference CPU path on this box's
-cores on a bounded rotation sample.  One JSON line on stdout (rank 0).
+rotation.  `cpu_baseline` times the reference CPU path (oracle port; rotation by the reference's own compiled
+_extensions.c when oracle/_ref travelled) on this box's cores on a bounded rotation sample: one persistent
+process per core, correlator built once per process outside the timed region, >= 8 rotations per process.
+At N > 1 the line also carries `merge_check` (the NCCL-merged grids of a sharded search equal the single-GPU
+grids bit for bit and the reference golden) and, at every N, `strong`: ONE 7416-rotation core-weighted search
+(configs[2]) sharded over the N ranks through CUDACorrelator.scan().  One JSON line on stdout (rank 0).
 """
 import argparse
 import ctypes
@@ -57,6 +61,43 @@ def make_inputs(workload):
     else:
         case = synth.config2(seed=0, core_weighted=w["cw"])
     return case
+
+
+def search_rotations(workload, count):
+    """`count` rotation matrices of the workload's search.  The 128^3 workloads use the reference's own 10 degree
+    set (7416 proportional orientations, stored with the full-search golden made by the real reference), repeated
+    when a run needs more; the other sizes have no stored set here and use seeded uniform random rotations."""
+    from powerfit_b200 import synth
+    path = os.path.join(ROOT, "tests", "golden", "scan_config2_128_full.npz")
+    if WORKLOADS[workload]["angle"] == "10deg" and os.path.exists(path):
+        full = np.load(path)["rotations"]
+        reps = (count + len(full) - 1) // len(full)
+        return np.ascontiguousarray(np.tile(full, (reps, 1, 1))[:count]), "c48 10deg set (7416 proportional orientations)"
+    return synth.random_rotations(count, seed=1), "seeded uniform random rotations"
+
+
+def default_batch(n):
+    """pfb_plan_create's default rotations per batch (csrc/api.cu)."""
+    per_pair = 6 * n ** 3 * 8
+    pairs = max(1, min(256 if per_pair <= (32 << 20) else 128, (24576 << 20) // per_pair))
+    return 2 * pairs
+
+
+def workload_config(w, world, rps, batch, rot_desc):
+    """The `config` object both arms print (the reference arm times a bounded sample of this workload)."""
+    n = w["n"]
+    nf = 3 if w["cw"] else 2
+    return {"workload": w["desc"], "shape": [n, n, n], "rotations_per_step_per_gpu": int(rps), "rotation_set": rot_desc,
+            "batch": int(batch), "mask": "core-weighted" if w["cw"] else "binary", "laplace": w["laplace"],
+            "parallelism": "rotation shards x%d + packed MAX all-reduce" % world,
+            "l2": "working set per batch (%.0f MB) exceeds the 126 MB L2; no flush needed"
+                  % (batch / 2 * (nf + 3) * 8 * n ** 3 / 1e6)}
+
+
+def default_rps(w):
+    n = w["n"]
+    # one step = one full rotational search of the named angle at 128^3 (7416 rotations); bounded blocks elsewhere
+    return {64: 2048, 128: w["full_R"], 256: 128, 192: 150}.get(n, 256)
 
 
 def peak_hbm():
@@ -121,52 +162,257 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(case, laplace, rotations, per_core=4, cores=None):
-    """Oracle port of the reference CPU path (PowerFitter._cpu_scan) on a bounded sample."""
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=False)
+# ----------------------------------------------------------------------------- CPU arm
+_CPU = {}
+
+
+def _cpu_init(target, template, mask, laplace, root):
+    """Pool initialiser: one correlator per process, built once (the reference's _cpu_scan builds one per
+    forked process too, powerfitter.py:110-122); rotation through the reference's own compiled C when it is there."""
+    if root not in sys.path:
+        sys.path.insert(0, root)
     from oracle import oracle as O
-    cores = cores or os.cpu_count() or 1
-    n = cores * per_core
-    sub = rotations[:n]
-    t0 = time.time()
-    O.parallel_scan(case.target, case.template, case.mask, sub, laplace=laplace, nproc=cores)
-    dt = time.time() - t0
-    return {"value": n / dt, "unit": "rotations/s", "cores": cores, "kind": "port",
-            "sample": "%d rotations (%d per process) of the same workload, oracle port of CPUCorrelator "
-                      "(numpy.fft backend, FP64), %d processes, %.1f s" % (n, per_core, cores, dt)}
+    ext = O.load_reference_extension()
+    rotate = None
+    if ext is not None:
+        def rotate(grid, rotmat, radius, out, nearest):
+            ext.rotate_grid3d(grid, np.ascontiguousarray(rotmat, dtype=np.float64), int(radius), out, bool(nearest))
+    c = O.OracleCorrelator(target, laplace=laplace, rotate=rotate)
+    c.template = template
+    c.mask = mask
+    _CPU["c"] = c
+
+
+def _cpu_block(rotations):
+    c = _CPU["c"]
+    c.rotations = rotations
+    c.scan()
+    return c.lcc, c.rot
+
+
+class CpuArm:
+    """The reference CPU search on this box's cores: `cores` persistent processes, contiguous rotation blocks
+    (powerfitter.py:95-108), strict-'>' merge in block order (:146-163)."""
+
+    def __init__(self, case, laplace, cores=None):
+        import multiprocessing as mp
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=False)
+        from oracle import oracle as O
+        self.O = O
+        self.kind = "reference" if O.load_reference_extension() is not None else "port"
+        self.cores = cores or os.cpu_count() or 1
+        self.shape = case.target.shape
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init,
+                                                initargs=(case.target, case.template, case.mask, laplace, ROOT))
+        self.pool.map(_cpu_block, [np.eye(3)[None]] * self.cores)       # every process has built its correlator
+
+    def step(self, rotations):
+        blocks = self.O.partition_rotations(len(rotations), self.cores)
+        t0 = time.perf_counter()
+        parts = self.pool.map(_cpu_block, [rotations[a:b] for a, b in blocks], chunksize=1)
+        self.O.combine_partials(parts, len(rotations) // self.cores, self.shape)
+        return time.perf_counter() - t0
+
+    def describe(self, n, per_core):
+        how = ("rotate_grid3d = the reference's own _extensions.c (oracle/_ref), FFTs = numpy.fft (the reference's "
+               "fallback without pyFFTW), conj_multiply/calc_lcc restated") if self.kind == "reference" else \
+              "oracle port of CPUCorrelator (numpy.fft backend)"
+        return ("%d rotations per step (%d per process x %d persistent processes, correlator and FT(map) built once "
+                "per process outside the timed region), FP64, %s" % (n, per_core, self.cores, how))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_per_core(n):
+    """Rotations per process and step: >= 8, more on small grids; ~10-30 s of CPU work in total."""
+    return 8 if n >= 128 else 48
+
+
+def cpu_baseline(case, laplace, rotations, n):
+    """Reference CPU path on a bounded sample of the same workload (one warm-up step, one timed step)."""
+    arm = CpuArm(case, laplace)
+    try:
+        per_core = cpu_per_core(n)
+        cnt = arm.cores * per_core
+        arm.step(rotations[:arm.cores])                    # warm-up: FFT plans, page faults
+        dt = arm.step(rotations[:cnt])
+        return {"value": cnt / dt, "unit": "rotations/s", "cores": arm.cores, "kind": arm.kind,
+                "sample": arm.describe(cnt, per_core) + ", %.1f s" % dt}
+    finally:
+        arm.close()
 
 
 def run_reference(args, w, rank, world, emit):
-    """--impl reference: the reference's CPU implementation (oracle port; the reference's own
-    Python needs its package, which cannot travel) on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores (the reference's
+    own Python package cannot travel; see CpuArm), on a bounded sample of our arm's workload per step."""
     if rank != 0:
         return
-    from powerfit_b200 import synth
     case = make_inputs(args.workload)
-    cores = os.cpu_count() or 1
-    per_core = 1 if w["n"] >= 128 else 4
-    n = cores * per_core
-    rots = synth.random_rotations(n * (args.steps + args.warmup), seed=1)
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=False)
-    from oracle import oracle as O
+    n = w["n"]
+    arm = CpuArm(case, w["laplace"])
+    per_core = cpu_per_core(n)
+    cnt = arm.cores * per_core
+    rots, rot_desc = search_rotations(args.workload, cnt * (args.steps + args.warmup))
     times = []
     for s in range(args.warmup + args.steps):
-        sub = rots[s * n:(s + 1) * n]
-        t0 = time.time()
-        O.parallel_scan(case.target, case.template, case.mask, sub, laplace=w["laplace"], nproc=cores)
+        dt = arm.step(rots[s * cnt:(s + 1) * cnt])
         if s >= args.warmup:
-            times.append(time.time() - t0)
+            times.append(dt)
+    arm.close()
     T = sum(times)
-    val = n * args.steps / T
-    sample = "%d rotations per step (%d per process x %d processes), oracle port of CPUCorrelator, numpy.fft FP64" % (
-        n, per_core, cores)
+    val = cnt * args.steps / T
+    sample = arm.describe(cnt, per_core)
     out = {"impl": "reference", "metric": "rotations/s (LCC search)", "value": val, "unit": "rotations/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": w["desc"], "rotations_per_step": n},
-           "cpu_baseline": {"value": val, "unit": "rotations/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": workload_config(w, world, args.rot_per_step or default_rps(w), args.batch or default_batch(n), rot_desc),
+           "cpu_baseline": {"value": val, "unit": "rotations/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
            "e2e": {"value": val, "unit": "rotations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
+
+
+# ----------------------------------------------------------------------------- multi-GPU checks
+def merge_check(dev, rank, world):
+    """Sharded CUDACorrelator.scan() (rotation blocks per rank + ONE NCCL MAX all-reduce on the packed keys) against
+    the unsharded scan on the same rank and against the reference golden.  (a) tests/golden/scan_32_plain.npz, the
+    any-shape pipeline, 216 rotations: golden tolerance (1e-4, rotation index where decided) and agreement with the
+    unsharded result; (b) 64 rotations of the 128^3 core-weighted workload on the fused pipeline: bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from powerfit_b200 import CUDACorrelator, synth
+    res = {}
+    g = np.load(os.path.join(ROOT, "tests", "golden", "scan_32_plain.npz"))
+    tgt, tmpl, msk = (g[k].astype(np.float64) for k in ("target", "template", "mask"))
+    out = {}
+    for shard in (True, False):
+        c = CUDACorrelator(tgt, device=dev, laplace=bool(g["laplace"]), shard=shard)
+        c.template, c.mask, c.rotations = tmpl, msk, g["rotations"]
+        c.scan()
+        out[shard] = (c.lcc.copy(), c.rot.copy())
+        del c
+    decided = (g["lcc"] - g["lcc2"]) > 1e-4
+    err = float(np.abs(out[True][0] - g["lcc"]).max())
+    res["golden_32"] = {"max_abs_dlcc": err, "rot_equal_where_decided": bool(np.array_equal(out[True][1][decided], g["rot"][decided])),
+                        "sharded_vs_single_max_abs": float(np.abs(out[True][0] - out[False][0]).max()),
+                        "sharded_vs_single_rot_equal_where_decided": bool(np.array_equal(out[True][1][decided], out[False][1][decided]))}
+    ok = err <= 1e-4 and res["golden_32"]["rot_equal_where_decided"] and \
+        res["golden_32"]["sharded_vs_single_max_abs"] <= 1e-5 and res["golden_32"]["sharded_vs_single_rot_equal_where_decided"]
+    case = synth.config2(seed=0, core_weighted=True)
+    rots, _ = search_rotations("config3", 7416)
+    sub = np.ascontiguousarray(rots[::7416 // 64][:64])
+    out = {}
+    for shard in (True, False):
+        c = CUDACorrelator(case.target, device=dev, laplace=False, shard=shard)
+        c.template, c.mask, c.rotations = case.template, case.mask, sub
+        c.scan()
+        out[shard] = (c.lcc.copy(), c.rot.copy())
+        fused = c.plan_info(6)
+        del c
+    same = bool(np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1]))
+    res["fused_128_64rot"] = {"bit_identical": same, "fused": int(fused), "nonzero": int((out[True][0] > 0).sum())}
+    ok = ok and same and res["fused_128_64rot"]["nonzero"] > 0
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["ok"] = bool(flag.item())
+    res["ranks"] = world
+    return res
+
+
+def strong_search(dev, rank, world, batch):
+    """ONE 10 degree search (7416 rotations) of the 128^3 core-weighted workload (BASELINE configs[2]) sharded over
+    the ranks through CUDACorrelator.scan(): contiguous blocks (powerfitter.py:95-108), packed MAX all-reduce,
+    unpack, download on every rank.  Correlator set-up (upload, FT(map), template preparation) is outside the
+    timed call, like the reference CLI's "Time for search".  Times are the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from powerfit_b200 import CUDACorrelator, synth
+    case = synth.config2(seed=0, core_weighted=True)
+    rots, rot_desc = search_rotations("config3", 7416)
+    c = CUDACorrelator(case.target, device=dev, laplace=False, batch=batch, shard=True)
+    c.template, c.mask, c.rotations = case.template, case.mask, rots
+    c.scan()                                             # warm-up (NCCL channels, first-use set-up)
+    best = None
+    for rep in range(3):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        c.scan()
+        dt = time.perf_counter() - t0
+        prof = dict(c.last_scan_profile)
+        vals = torch.tensor([dt, prof["search_ms"], prof["allreduce_ms"], prof["unpack_download_ms"]], device=dev,
+                            dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        vals = [float(v) for v in vals.tolist()]
+        if best is None or vals[0] < best[0]:
+            best = vals
+    checksum = int(np.count_nonzero(c.lcc)), float(c.lcc.max()), int(c.rot.reshape(-1)[int(np.argmax(c.lcc))])
+    return {"workload": "ONE 7416-rotation search, 128^3 core-weighted (configs[2]), sharded over %d rank(s)" % world,
+            "rotation_set": rot_desc, "rotations": 7416, "rotations_per_rank": int(c.last_scan_profile["rotations"]),
+            "seconds": best[0], "rotations_per_s": 7416 / best[0], "search_ms": best[1], "allreduce_ms": best[2],
+            "unpack_download_ms": best[3], "timing": "wall clock of scan() between barriers, max over ranks, best of 3; "
+            "split from CUDA events on the scan stream",
+            "result": {"nonzero": checksum[0], "lcc_max": checksum[1], "rot_at_max": checksum[2]}}
+
+
+def kernel_split(corr, lib, run_step):
+    """Per-kernel-class device time of one extra, untimed step (events around every launch; the scan then keeps
+    all kernels on one stream so that the classes do not overlap)."""
+    import torch
+    from powerfit_b200 import _lib
+    kernels = {}
+    _lib.check(lib.pfb_profile(corr._plan, 1))
+    run_step()
+    torch.cuda.synchronize(corr._device)
+    _lib.check(lib.pfb_profile(corr._plan, 0))
+    cls = 0
+    while True:
+        kms, kn, name = ctypes.c_double(), ctypes.c_int64(), ctypes.c_char_p()
+        if lib.pfb_profile_read(corr._plan, cls, ctypes.byref(kms), ctypes.byref(kn), ctypes.byref(name)) != 0:
+            break
+        if kn.value:
+            kernels[name.value.decode()] = {"ms": kms.value, "launches": kn.value}
+        cls += 1
+    return kernels
+
+
+def extra_config(workload, dev, steps=2, warmup=1):
+    """Resident-input throughput of another BASELINE config, measured in this process (short run)."""
+    import torch
+    from powerfit_b200 import CUDACorrelator, _lib
+    w = WORKLOADS[workload]
+    n = w["n"]
+    case = make_inputs(workload)
+    rps = default_rps(w)
+    rots, rot_desc = search_rotations(workload, rps * (steps + warmup))
+    corr = CUDACorrelator(case.target, device=dev, laplace=w["laplace"])
+    corr.template, corr.mask, corr.rotations = case.template, case.mask, rots
+    nf = 2 if corr._mask_binary else 3
+    S = 8 * n * n * (n // 2 + 1)
+    stream = torch.cuda.current_stream(dev)
+    for i in range(warmup):
+        corr.scan_device(i * rps, (i + 1) * rps, reset=(i == 0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for i in range(warmup, warmup + steps):
+        corr.scan_device(i * rps, (i + 1) * rps, reset=False)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    value = rps * steps / (ms / 1e3)
+    peak, _ = peak_hbm()
+    kern = kernel_split(corr, _lib.load(), lambda: corr.scan_device(0, rps, reset=False))
+    out = {"workload": w["desc"], "rotations_per_step": rps, "steps": steps, "warmup": warmup, "rotation_set": rot_desc,
+           "value": value, "unit": "rotations/s", "batch": corr.plan_info(4), "mask": "binary" if nf == 2 else "core-weighted",
+           "bytes_per_rotation": (2 * nf + 6) * S, "step_frac": value * (2 * nf + 6) * S / 1e9 / peak,
+           "us_per_rotation": {k: 1e3 * v["ms"] / rps for k, v in kern.items()}}
+    del corr
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -179,7 +425,8 @@ def main():
     ap.add_argument("--rot-per-step", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-kernels", action="store_true", help="extra untimed step with per-kernel events")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip merge_check / strong / the other configs / api_search (kernel experiments)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -200,7 +447,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from powerfit_b200 import CUDACorrelator, _lib, synth
+    from powerfit_b200 import CUDACorrelator, _lib
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
@@ -209,13 +456,22 @@ def main():
     dev = torch.device("cuda", local)
     lib = _lib.load()
 
+    # ---------------- N > 1: the merged result is checked before anything is timed
+    mcheck = None
+    if world > 1 and not args.no_extras:
+        mcheck = merge_check(dev, rank, world)
+        if not mcheck["ok"]:
+            if rank == 0:
+                emit({"error": "merge_check failed: sharded search differs from the single-GPU search", "merge_check": mcheck})
+            dist.destroy_process_group()
+            sys.exit(1)
+
     case = make_inputs(args.workload)
     n = w["n"]
     V = n ** 3
-    # one step = one full rotational search of the named angle at 128^3 (7416 rotations); bounded blocks elsewhere
-    rps = args.rot_per_step or {64: 2048, 128: w["full_R"], 256: 128, 192: 128}.get(n, 256)
+    rps = args.rot_per_step or default_rps(w)
     total_steps = args.warmup + args.steps
-    rots = synth.random_rotations(rps * total_steps * world + 8, seed=1)
+    rots, rot_desc = search_rotations(args.workload, rps * total_steps * world + 8)
 
     corr = CUDACorrelator(case.target, device=dev, laplace=w["laplace"], batch=args.batch)
     corr.template = case.template
@@ -296,14 +552,13 @@ def main():
     # ---------------- the user-level call: CUDACorrelator from host float64 arrays to host lcc/rot grids
     # (plan creation, FP64 preparation on the device, search, download), timed once per preparation mode
     api = {}
-    if rank == 0 or world > 1:
+    if not args.no_extras:
         sub = rots[:rps]
         for rep in range(3):                     # best of three per mode (the first pays one-time CUDA set-up)
             for mode in ("device", "host"):
                 torch.cuda.synchronize(dev)
                 t0 = time.perf_counter()
                 c2 = CUDACorrelator(case.target, device=dev, laplace=w["laplace"], batch=args.batch, prep=mode)
-                c2.shard = False
                 c2.template, c2.mask, c2.rotations = case.template, case.mask, sub
                 c2.scan()
                 dt = time.perf_counter() - t0
@@ -313,19 +568,7 @@ def main():
                 del c2
 
     # ---------------- per-kernel split (extra, untimed): events around every launch
-    kernels = {}
-    _lib.check(lib.pfb_profile(corr._plan, 1))
-    step(total_steps - 1)
-    torch.cuda.synchronize(dev)
-    _lib.check(lib.pfb_profile(corr._plan, 0))
-    cls = 0
-    while True:
-        kms, kn, name = ctypes.c_double(), ctypes.c_int64(), ctypes.c_char_p()
-        if lib.pfb_profile_read(corr._plan, cls, ctypes.byref(kms), ctypes.byref(kn), ctypes.byref(name)) != 0:
-            break
-        if kn.value:
-            kernels[name.value.decode()] = {"ms": kms.value, "launches": kn.value}
-        cls += 1
+    kernels = kernel_split(corr, lib, lambda: step(total_steps - 1))
     tot_ms = sum(k["ms"] for k in kernels.values()) or 1.0
     top = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     peak, peak_src = peak_hbm()
@@ -337,6 +580,7 @@ def main():
             "traffic_source": None,
             "step_achieved": value / world * B_rot / 1e9, "step_frac": value / world * B_rot / 1e9 / peak,
             "bytes_per_rotation": B_rot}
+    batch = corr.plan_info(4)
     if top:
         k = kernels[top]
         ach = alg.get(top, 0) * rps / (k["ms"] / 1e3) / 1e9
@@ -344,36 +588,59 @@ def main():
         # capture, rescaled to the rotations one launch of this run processes); null if there is no capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload][top]
-            roof["traffic"] = tr["dram_bytes_per_launch"] * min(corr.plan_info(4), rps) / tr["rotations_per_launch"]
+            roof["traffic"] = tr["dram_bytes_per_launch"] * min(batch, rps) / tr["rotations_per_launch"]
             roof["traffic_source"] = tr["source"]
         except Exception:
             pass
         roof.update({"kernel": top, "achieved": ach, "frac": ach / peak,
                      "kernel_share_of_step": k["ms"] / tot_ms,
                      "kernel_ms_per_launch": k["ms"] / k["launches"],
-                     "kernels": {n_: {"ms_per_step": v["ms"], "launches": v["launches"], "share": v["ms"] / tot_ms}
+                     "kernels": {n_: {"ms_per_step": v["ms"], "launches": v["launches"], "share": v["ms"] / tot_ms,
+                                      "us_per_rotation": 1e3 * v["ms"] / rps,
+                                      "frac_of_own_bytes": alg.get(n_, 0) * rps / (v["ms"] / 1e3) / 1e9 / peak}
                                  for n_, v in kernels.items()}})
     else:
         roof.update({"achieved": roof["step_achieved"], "frac": roof["step_frac"]})
 
+    del corr
+    torch.cuda.empty_cache()
+
+    # ---------------- ONE full search sharded over the ranks (strong scaling), every N
+    strong = None
+    if not args.no_extras:
+        strong = strong_search(dev, rank, world, args.batch)
+
+    # ---------------- the other BASELINE configs, measured in this process (N = 1 only)
+    others = {}
+    if world == 1 and not args.no_extras:
+        for name in ("config1", "config3", "config5", "config4"):
+            if name == args.workload:
+                continue
+            try:
+                others[name] = extra_config(name, dev)
+            except Exception as exc:       # never sink the headline
+                others[name] = {"error": repr(exc)}
+
     out = {"metric": "rotations/s (LCC search)", "value": value, "unit": "rotations/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": w["desc"], "shape": [n, n, n], "rotations_per_step_per_gpu": rps,
-                      "batch": corr.plan_info(4), "mask": "binary" if nf == 2 else "core-weighted",
-                      "laplace": w["laplace"], "parallelism": "rotation shards x%d + packed MAX all-reduce" % world,
-                      "l2": "working set per batch (%.0f MB) exceeds the 126 MB L2; no flush needed"
-                            % (corr.plan_info(4) / 2 * (nf + 3) * 8 * V / 1e6)},
+           "config": workload_config(w, world, rps, batch, rot_desc),
            "e2e": {"value": e2e_val, "unit": "rotations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "call": "pfb_search_host (host buffers in/out, includes FT(map) setup)"},
            "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
            "api_search": dict(api, call="CUDACorrelator(target) -> .template/.mask/.rotations -> .scan() from host "
                                         "float64 arrays, one search of rotations_per_step_per_gpu rotations, "
                                         "per preparation mode (device FP64 kernels / host numpy+scipy)")}
+    if mcheck is not None:
+        out["merge_check"] = mcheck
+    if strong is not None:
+        out["strong"] = strong
+    if others:
+        out["configs"] = others
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = cpu_baseline(case, w["laplace"], rots, per_core=2 if n >= 128 else 8)
+                out["cpu_baseline"] = cpu_baseline(case, w["laplace"], rots, n)
             except Exception as exc:       # the baseline must never sink the GPU number
                 out["cpu_baseline"] = {"value": None, "error": repr(exc)}
         emit(out)

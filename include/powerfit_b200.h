@@ -74,6 +74,14 @@ int pfb_set_target(pfb_plan *plan, const float *target, const uint8_t *lcc_mask,
 int pfb_set_template(pfb_plan *plan, const float *tmpl, const float *mask, float norm_factor,
                      int mask_is_binary, void *stream);
 
+/* Several templates against ONE map (BASELINE configs[4]: "a batch of 4 distinct templates"; the reference
+ * CLI builds one PowerFitter -- and recomputes FT(map), FT(map^2) -- per template, powerfit.py:245-282).
+ * A plan has template slots: pfb_template_slots grows their number (slot 0 always exists),
+ * pfb_select_template makes one current; pfb_set_template / pfb_prepare_template fill the current slot and
+ * pfb_scan / pfb_search_host search with it.  The map spectra, lcc_mask and work buffers are shared. */
+int pfb_template_slots(pfb_plan *plan, int nslots);
+int pfb_select_template(pfb_plan *plan, int slot);
+
 /* The same two setters with the reference's one-time preparation done on the device in FP64
  * (SURVEY.md 8f rows N3/N2).  All pointers DEVICE unless noted.
  * pfb_prepare_target = BaseCorrelator.__init__ + GPUCorrelator.__init__ (powerfitter.py:169-180,

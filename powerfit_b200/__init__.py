@@ -6,7 +6,7 @@ C ABI (`include/powerfit_b200.h`), driven from Python.  Importing the package do
 need a GPU; constructing a correlator does (there is no CPU fallback).
 """
 from ._lib import PowerfitB200Error, build, load  # noqa: F401
-from .correlator import CUDACorrelator, shard_bounds  # noqa: F401
+from .correlator import CUDACorrelator, MultiTemplateCorrelator, shard_bounds, template_work_items  # noqa: F401
 from .powerfitter import PowerFitter  # noqa: F401
 from .analyzer import Analyzer  # noqa: F401
 from . import shapes, pyramid, target_prep  # noqa: F401

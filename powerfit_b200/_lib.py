@@ -23,7 +23,7 @@ SYMBOLS = ["pfb_version", "pfb_last_error", "pfb_plan_create", "pfb_plan_destroy
            "pfb_merge_best", "pfb_profile", "pfb_profile_read", "pfb_rotate", "pfb_fft3_c2c", "pfb_lcc_take_best", "pfb_search_host",
            "pfb_lcc_max", "pfb_peak_candidates", "pfb_prepare_target", "pfb_prepare_template",
            "pfb_blur_points", "pfb_dilate_points", "pfb_core_indices",
-           "pfb_gaussian_filter", "pfb_zoom_linear"]
+           "pfb_gaussian_filter", "pfb_zoom_linear", "pfb_template_slots", "pfb_select_template"]
 
 _lib = None
 
@@ -45,13 +45,18 @@ def build(force=False, verbose=False):
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    # link into a scratch name and rename: a reader (a loader, a snapshot of the tree) never sees a partial file
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise PowerfitB200Error("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH
@@ -78,6 +83,8 @@ def load():
     lib.pfb_set_template.argtypes = [vp, vp, vp, f32, i32, vp]
     lib.pfb_prepare_target.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.pfb_prepare_template.argtypes = [vp, vp, vp, i32, vp, vp, c.POINTER(c.c_double), c.POINTER(i32), vp]
+    lib.pfb_template_slots.argtypes = [vp, i32]
+    lib.pfb_select_template.argtypes = [vp, i32]
     lib.pfb_best_init.argtypes = [vp, vp, vp]
     lib.pfb_scan.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.pfb_unpack.argtypes = [vp, vp, vp, vp, vp]

@@ -157,8 +157,8 @@ class Analyzer(object):
             a = np.asarray(corr)
             if a.dtype != np.float32:
                 raise TypeError("corr must be float32 (the dtype the GPU search returns), got %s" % a.dtype)
-            dev = torch.device("cuda", 0 if self._device is None else self._device) \
-                if not isinstance(self._device, torch.device) else self._device
+            from .correlator import _resolve_device
+            dev = _resolve_device(self._device)               # LOCAL_RANK, then the current device
             d = torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(dev)
         n = d.numel()
         with torch.cuda.device(dev):

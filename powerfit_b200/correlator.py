@@ -103,8 +103,12 @@ def _resolve_device(device):
 class CUDACorrelator(object):
     """B200 implementation of the local cross-correlation search."""
 
-    def __init__(self, target, device=None, laplace=False, batch=0, prep="device", pad=False):
-        """``pad=True`` (opt-in, not reference behaviour): zero-pad the map to the next cubic grid that has
+    def __init__(self, target, device=None, laplace=False, batch=0, prep="device", pad=False, shard=False,
+                 group=None):
+        """``shard=True`` (opt-in): split the rotation list over the ranks of the torch.distributed process
+        group ``group`` (default: the world group) and merge with one MAX all-reduce, see ``scan``.
+
+        ``pad=True`` (opt-in, not reference behaviour): zero-pad the map to the next cubic grid that has
         a fused pipeline (64, 128, 192 or 256 voxels) and crop the results back.  The result is exactly
         the search on the padded map -- what the reference computes when its own `extend` step
         (powerfit.py:230-233) is given that size -- and about ten times faster than the any-shape pipeline;
@@ -138,8 +142,10 @@ class CUDACorrelator(object):
         self._lcc = None
         self._rot = None
         self.progress = False
-        self.shard = True           # split rotations over torch.distributed ranks when initialised
+        self.shard = bool(shard)    # split rotations over torch.distributed ranks (every rank must call scan())
+        self.group = group
         self.last_scan_seconds = None
+        self.last_scan_profile = None
 
         self._device = _resolve_device(device)
         self._plan = ctypes.c_void_p()
@@ -334,33 +340,47 @@ class CUDACorrelator(object):
                                        self._best.data_ptr(), s))
 
     def scan(self):
-        """GPUCorrelator.scan (powerfitter.py:513-538).  With an initialised
-        torch.distributed process group (and ``self.shard``) each rank searches its
-        contiguous block of the rotation list and the packed best grids are merged by a
-        single integer MAX all-reduce; every rank ends with the full result."""
+        """GPUCorrelator.scan (powerfitter.py:513-538).  With ``self.shard`` set and an initialised
+        torch.distributed process group each rank searches its contiguous block of the rotation list
+        (powerfitter.py:95-108) and the packed best grids are merged by a single integer MAX all-reduce
+        (the order-preserving key reproduces the reference's merge, powerfitter.py:146-163); every rank
+        ends with the full result.  EVERY rank of the group must call scan() with the same target,
+        template, mask and rotations -- sharding is therefore opt-in (``shard=True`` in the constructor
+        or ``PowerFitter(..., shard=True)``); without it a rank searches the whole list on its own.
+        ``last_scan_profile`` holds the device-timed split of the call (search / all-reduce / unpack+download)."""
         torch = self._torch
         t0 = time()
         nrot = 0 if self._rotations is None else self._rotations.shape[0]
         world, rank = 1, 0
         dist = torch.distributed
         if self.shard and dist.is_available() and dist.is_initialized():
-            world, rank = dist.get_world_size(), dist.get_rank()
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         lo, hi = shard_bounds(nrot, world, rank)
-        best = self.scan_device(lo, hi)
-        if world > 1:
-            dist.all_reduce(best, op=dist.ReduceOp.MAX)
+        stream = torch.cuda.current_stream(self._device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         with torch.cuda.device(self._device):
+            ev[0].record(stream)
+            best = self.scan_device(lo, hi)
+            ev[1].record(stream)
+            if world > 1:
+                dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+            ev[2].record(stream)
             lcc = torch.empty(self._shape, dtype=torch.float32, device=self._device)
             rot = torch.empty(self._shape, dtype=torch.int32, device=self._device)
             _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
                                              self._stream()))
             self._lcc = lcc.cpu().numpy()             # powerfitter.py:536-537
             self._rot = rot.cpu().numpy()
+            ev[3].record(stream)
+            ev[3].synchronize()
             if self._crop is not None:
                 nz, ny, nx = self._crop
                 self._lcc = np.ascontiguousarray(self._lcc[:nz, :ny, :nx])
                 self._rot = np.ascontiguousarray(self._rot[:nz, :ny, :nx])
         self.last_scan_seconds = time() - t0
+        self.last_scan_profile = {"rotations": int(hi - lo), "world": int(world),
+                                  "search_ms": ev[0].elapsed_time(ev[1]), "allreduce_ms": ev[1].elapsed_time(ev[2]),
+                                  "unpack_download_ms": ev[2].elapsed_time(ev[3])}
 
     @staticmethod
     def _print_progress(n, nrot, time0):               # powerfitter.py:540-547
@@ -412,3 +432,105 @@ class CUDACorrelator(object):
             _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
                                              self._stream()))
             return lcc.cpu().numpy(), rot.cpu().numpy(), best
+
+
+def template_work_items(ntemplates, nrot, world):
+    """(template, lo, hi) work items of a multi-template search for `world` ranks: every template's rotation list
+    is cut into K = world / gcd(T, world) contiguous blocks (powerfitter.py:95-108 per template), so that the
+    T K items divide evenly over the ranks; item i belongs to rank i % world."""
+    from math import gcd
+    k = world // gcd(ntemplates, world)
+    items = []
+    for t in range(ntemplates):
+        for b in range(k):
+            lo, hi = shard_bounds(nrot, k, b)
+            items.append((t, lo, hi))
+    return items
+
+
+class MultiTemplateCorrelator(CUDACorrelator):
+    """Several templates against ONE map (BASELINE configs[4]: fitting a batch of sub-units).
+
+    The reference runs one ``PowerFitter`` -- one correlator, one FT(map), FT(map^2) -- per template
+    (powerfit.py:245-282).  Here the plan keeps one template slot per sub-unit (``pfb_template_slots`` /
+    ``pfb_select_template``) and shares the map spectra, lcc_mask and work buffers between them; every slot is
+    filled through the same ``.template`` / ``.mask`` setters as a single-template correlator (same preparation,
+    same errors) and gives exactly the result a fresh ``CUDACorrelator`` gives for that template.
+
+    ``scan_all()`` searches every template over ``.rotations``.  With ``shard=True`` under torch.distributed the
+    (template, rotation block) work items are dealt over the ranks and ALL templates' packed best grids are
+    merged by one MAX all-reduce of the [T, V] int64 tensor."""
+
+    _SLOT_ATTRS = ("_template_h", "_template_set", "_mask", "_mask_binary", "_norm_factor", "_d_template", "_d_mask")
+
+    def __init__(self, target, ntemplates, **kw):
+        super().__init__(target, **kw)
+        if ntemplates < 1:
+            raise ValueError("ntemplates must be positive")
+        _lib.check(self._libh.pfb_template_slots(self._plan, int(ntemplates)))
+        self.ntemplates = int(ntemplates)
+        self._slot = 0
+        self._slot_state = [None] * self.ntemplates
+        self.lccs = [None] * self.ntemplates
+        self.rots = [None] * self.ntemplates
+
+    def select(self, slot):
+        if not 0 <= slot < self.ntemplates:
+            raise ValueError("no such template slot")
+        if slot == self._slot:
+            return
+        self._slot_state[self._slot] = {k: getattr(self, k, None) for k in self._SLOT_ATTRS}
+        _lib.check(self._libh.pfb_select_template(self._plan, int(slot)))
+        state = self._slot_state[slot] or {"_template_h": None, "_template_set": False, "_mask": None,
+                                           "_mask_binary": None, "_norm_factor": None, "_d_template": None,
+                                           "_d_mask": None}
+        for k, v in state.items():
+            setattr(self, k, v)
+        self._slot = slot
+
+    def set_template(self, slot, template, mask):
+        self.select(slot)
+        self.template = template
+        self.mask = mask
+
+    def scan_all(self):
+        torch = self._torch
+        if self._rotations is None:
+            raise ValueError("First set the template, mask, and rotations.")
+        t0 = time()
+        nrot, T = self._rotations.shape[0], self.ntemplates
+        world, rank = 1, 0
+        dist = torch.distributed
+        if self.shard and dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        V = int(np.prod(self._shape))
+        with torch.cuda.device(self._device):
+            best = torch.empty((T, V), dtype=torch.int64, device=self._device)
+            for t in range(T):
+                _lib.check(self._libh.pfb_best_init(self._plan, best[t].data_ptr(), self._stream()))
+            mine = template_work_items(T, nrot, world)[rank::world]
+            done = 0
+            for t, lo, hi in mine:
+                self.select(t)
+                if not self._template_set or self._mask is None:
+                    raise ValueError("First set the template, mask, and rotations.")
+                sub = self._rotations[lo:hi]
+                _lib.check(self._libh.pfb_scan(self._plan, sub.ctypes.data_as(ctypes.c_void_p), hi - lo, lo,
+                                               best[t].data_ptr(), self._stream()))
+                done += hi - lo
+            if world > 1:
+                dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+            lcc = torch.empty((T,) + tuple(self._shape), dtype=torch.float32, device=self._device)
+            rot = torch.empty((T,) + tuple(self._shape), dtype=torch.int32, device=self._device)
+            for t in range(T):
+                _lib.check(self._libh.pfb_unpack(self._plan, best[t].data_ptr(), lcc[t].data_ptr(), rot[t].data_ptr(),
+                                                 self._stream()))
+            lcc, rot = lcc.cpu().numpy(), rot.cpu().numpy()
+        for t in range(T):
+            self.lccs[t], self.rots[t] = lcc[t], rot[t]
+            if self._crop is not None:
+                nz, ny, nx = self._crop
+                self.lccs[t] = np.ascontiguousarray(lcc[t][:nz, :ny, :nx])
+                self.rots[t] = np.ascontiguousarray(rot[t][:nz, :ny, :nx])
+        self.last_scan_seconds = time() - t0
+        self.last_scan_rotations = done

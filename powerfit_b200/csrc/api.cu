@@ -52,6 +52,15 @@ static void profile_collect(Plan *p) {
     p->prof.clear();
 }
 
+static void slot_save(Plan *p, TemplateSlot &t) {
+    t.tmpl = p->tmpl; t.mask = p->mask; t.tmplq = p->tmplq; t.norm_factor = p->norm_factor; t.nsig = p->nsig;
+    t.rs = p->rs; t.rs2 = p->rs2; t.ymask = p->ymask; t.nmask = p->nmask; t.have_template = p->have_template;
+}
+static void slot_load(Plan *p, const TemplateSlot &t) {
+    p->tmpl = t.tmpl; p->mask = t.mask; p->tmplq = t.tmplq; p->norm_factor = t.norm_factor; p->nsig = t.nsig;
+    p->rs = t.rs; p->rs2 = t.rs2; p->ymask = t.ymask; p->nmask = t.nmask; p->have_template = t.have_template;
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -165,6 +174,7 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
         p->batch = ((p->batch / 2) + 1) & ~1;
     }
     PFB_ALLOC(p->best_scratch, sizeof(int64_t) * p->V);
+    PFB_ALLOC(p->prep_scratch, kPrepScratchBytes);
     p->fused = fused_supported(nz, ny, nx);
     if (const char *e = getenv("PFB_FUSED")) p->fused = p->fused && atoi(e) != 0;
     if (p->fused) {
@@ -175,6 +185,7 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
         PFB_ALLOC(p->tmplq, sizeof(float4) * p->V);
     }
 #undef PFB_ALLOC
+    p->slots.resize(1);
     if ((rc = ensure_rot_capacity(p, 1024))) return fail(rc);
     if (p->fused && (rc = fused_init(p))) return fail(rc);
     if (p->fused) {
@@ -196,8 +207,15 @@ int pfb_plan_destroy(pfb_plan *h) {
     if (!h) return PFB_OK;
     Plan *p = &h->p;
     DeviceGuard guard(p->device);
+    if (!p->slots.empty()) slot_save(p, p->slots[p->cur]);
+    for (size_t i = 0; i < p->slots.size(); ++i) {
+        if ((int)i == p->cur) continue;           // the active slot's buffers are freed through the Plan fields
+        if (p->slots[i].tmpl) cudaFree(p->slots[i].tmpl);
+        if (p->slots[i].mask) cudaFree(p->slots[i].mask);
+        if (p->slots[i].tmplq) cudaFree(p->slots[i].tmplq);
+    }
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->tmplq,
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->prep_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->tmplq,
                     p->cls_twN, p->cls_twM, p->cls_twh, p->cls_fold};
     for (void *q : ptrs)
         if (q) cudaFree(q);
@@ -224,6 +242,38 @@ int pfb_plan_info(const pfb_plan *h, int what, int64_t *value) {
         case 7: *value = (int64_t)(p->launches & 0x7FFFFFFF); break;
         default: set_error("pfb_plan_info: unknown field"); return PFB_ERR_INVALID;
     }
+    return PFB_OK;
+}
+
+int pfb_template_slots(pfb_plan *h, int nslots) {
+    PFB_REQUIRE(h, "pfb_template_slots: NULL plan");
+    PFB_REQUIRE(nslots >= 1 && nslots <= 64, "pfb_template_slots: between 1 and 64 slots");
+    Plan *p = &h->p;
+    DeviceGuard guard(p->device);
+    while ((int)p->slots.size() < nslots) {
+        TemplateSlot t;
+        if (cudaMalloc(&t.tmpl, sizeof(float) * p->V) != cudaSuccess || cudaMalloc(&t.mask, sizeof(float) * p->V) != cudaSuccess ||
+            (p->fused && cudaMalloc(&t.tmplq, sizeof(float4) * p->V) != cudaSuccess)) {
+            if (t.tmpl) cudaFree(t.tmpl);
+            if (t.mask) cudaFree(t.mask);
+            if (t.tmplq) cudaFree(t.tmplq);
+            cudaGetLastError();
+            set_error("pfb_template_slots: out of device memory");
+            return PFB_ERR_CUDA;
+        }
+        p->slots.push_back(t);
+    }
+    return PFB_OK;
+}
+
+int pfb_select_template(pfb_plan *h, int slot) {
+    PFB_REQUIRE(h, "pfb_select_template: NULL plan");
+    Plan *p = &h->p;
+    PFB_REQUIRE(slot >= 0 && slot < (int)p->slots.size(), "pfb_select_template: no such slot (pfb_template_slots first)");
+    if (slot == p->cur) return PFB_OK;
+    slot_save(p, p->slots[p->cur]);
+    slot_load(p, p->slots[slot]);
+    p->cur = slot;
     return PFB_OK;
 }
 

@@ -58,6 +58,7 @@ struct Fft1D {
 bool factorize(int n, Fft1D *out);   // radices from {8,4,2,3,5,7}; false if not smooth
 
 struct Plan;
+constexpr size_t kPrepScratchBytes = 32768;
 
 // kernel classes for the optional per-kernel timing (pfb_profile*)
 enum KernelClass { KC_ROTATE = 0, KC_FFT_X, KC_FFT_Y, KC_FFT_Z, KC_MULTIPLY, KC_LCC, KC_FUSED_A, KC_FUSED_B,
@@ -103,6 +104,19 @@ int cls_a(Plan *p, int first, int count, cudaStream_t s);
 int cls_b(Plan *p, int count, float2 *X2, cudaStream_t s);
 int cls_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s);
 
+// Per-template state of a plan.  A plan owns the map (FT(f), FT(f^2), lcc_mask) and the work buffers; the
+// template-dependent buffers and parameters live in slots so that several templates can be searched against
+// the same map (BASELINE configs[4]: a batch of sub-unit templates).  The active slot is mirrored in the Plan
+// fields of the same names; pfb_select_template swaps pointers, nothing is copied.
+struct TemplateSlot {
+    float *tmpl = nullptr, *mask = nullptr;
+    float4 *tmplq = nullptr;
+    float norm_factor = 0.f;
+    int nsig = 2, rs = 0, rs2 = 0;
+    unsigned ymask = 0, nmask = 0;
+    bool have_template = false;
+};
+
 struct Plan {
     int nz = 0, ny = 0, nx = 0, rmax = 0, device = 0;
     long V = 0;
@@ -135,6 +149,9 @@ struct Plan {
     double *rot_dev = nullptr;
     long rot_cap = 0;
     int64_t *best_scratch = nullptr;              // used by pfb_search_host
+    void *prep_scratch = nullptr;                 // partial sums of the FP64 template preparation (prep.cu)
+    std::vector<TemplateSlot> slots;              // slots[cur] is stale while it is the active one
+    int cur = 0;
     // side stream of the fused scan: kernel A of the next batch runs next to kernel C of the current one
     cudaStream_t side = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;

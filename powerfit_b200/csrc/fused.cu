@@ -818,12 +818,21 @@ static int fused_back_tma(Plan *p, int first, int count, int rot_index_offset, i
     }
     constexpr int per_sm = NBUF == 1 ? 6 : (NBUF == 2 ? 4 : 3);
     const int tiles = (N / 16) * N;
-    // enough CTAs for ~4 waves of resident CTAs: split the pair loop into chunks
-    int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * per_sm + tiles - 1) / tiles));
-    int ppc = (npairs + chunks - 1) / chunks;
+    // split the pair loop into chunks so that the CTAs fill whole waves of resident CTAs (a 4.6-wave launch
+    // idles 8 % of the machine in its last wave); at least 8 pairs per CTA amortise its set-up and its atomics.
+    // Measured at 128^3, 128 pairs: 32 pairs per chunk 4.59 us/rotation, 22 -> 4.51, 10 -> 4.52, 64 -> 5.08.
+    const int slots = p->sm_count * per_sm;
+    int ppc = std::max(1, npairs);
+    double best_eff = -1.0;
+    for (int cand = std::min(npairs, 32); cand >= std::min(npairs, 8); --cand) {
+        const double waves = (double)tiles * ((npairs + cand - 1) / cand) / slots;
+        const double eff = waves / std::ceil(waves);
+        if (waves >= 3.0 && eff > best_eff + 1e-9) { best_eff = eff; ppc = cand; }
+    }
+    if (best_eff < 0) ppc = std::max(1, std::min(npairs, 8));
     static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
     if (ppc_env > 0) ppc = ppc_env;
-    chunks = (npairs + ppc - 1) / ppc;
+    const int chunks = (npairs + ppc - 1) / ppc;
     LaunchScope ls(p, KC_FUSED_C, s);
     fused_ifftx_lcc_tma_kernel<N, NBUF><<<dim3(N / 16, N, chunks), 64, smem_c_tma<N>(NBUF), s>>>(
         p->tmapC, p->mbits, p->norm_factor, rot_index_offset + first, count, ppc, best, p->twdN);
@@ -882,12 +891,19 @@ int fused_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, 
 // X1, and B(i+1) waits for A(i+1) and -- by stream order -- for C(i), the last reader of X2.  Per-kernel
 // profiling (events around every launch) keeps everything on one stream so that the classes do not overlap.
 int fused_scan(Plan *p, int R, int rot_index_offset, int64_t *best, cudaStream_t s) {
-    static const bool overlap_env = getenv("PFB_OVERLAP") ? atoi(getenv("PFB_OVERLAP")) != 0 : true;
+    // Off by default: measured at 128^3 the two-stream schedule is 0.6 % SLOWER (53.3k -> 52.9k rotations/s).
+    // Kernel C's six CTAs per SM hold every register and 216 KB of shared memory, so kernel A's CTAs only get
+    // on an SM when C's last wave drains -- there is no idle resource for the overlap to use.
+    static const bool overlap_env = getenv("PFB_OVERLAP") ? atoi(getenv("PFB_OVERLAP")) != 0 : false;
     const bool overlap = overlap_env && !p->profile && p->side != nullptr && R > p->batch;
     int rc;
+    // equal-size batches (even, so that rotation pairs never straddle two batches): a 927-rotation shard runs as
+    // 4 x 232 rather than 3 x 256 + 159
+    const int nbatch = (R + p->batch - 1) / p->batch;
+    const int per = std::min(p->batch, (((R + nbatch - 1) / nbatch) + 1) & ~1);
     if (!overlap) {
-        for (int first = 0; first < R; first += p->batch) {
-            const int count = std::min(p->batch, R - first);
+        for (int first = 0; first < R; first += per) {
+            const int count = std::min(per, R - first);
             if ((rc = fused_a(p, first, count, s))) return rc;
             if ((rc = fused_b(p, count, p->B, s))) return rc;
             if ((rc = fused_c(p, first, count, rot_index_offset, best, p->B, s))) return rc;
@@ -896,8 +912,8 @@ int fused_scan(Plan *p, int R, int rot_index_offset, int64_t *best, cudaStream_t
     }
     // the side stream joins after everything already queued on s (rotation upload, template set-up)
     PFB_CUDA(cudaEventRecord(p->ev_b, s));
-    for (int first = 0; first < R; first += p->batch) {
-        const int count = std::min(p->batch, R - first);
+    for (int first = 0; first < R; first += per) {
+        const int count = std::min(per, R - first);
         PFB_CUDA(cudaStreamWaitEvent(p->side, p->ev_b, 0));
         if ((rc = fused_a(p, first, count, p->side))) return rc;
         PFB_CUDA(cudaEventRecord(p->ev_a, p->side));

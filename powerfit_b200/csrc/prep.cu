@@ -197,7 +197,8 @@ int prep_target(Plan *p, const double *target, int laplace, float *f_out, uint8_
 int prep_template(Plan *p, const double *tmpl, const double *mask, int laplace, float *t_out, float *m_out,
                   double *norm_factor, int *mask_is_binary, cudaStream_t s) {
     double *work = reinterpret_cast<double *>(p->A);                          // V doubles of the forward work buffer
-    Stat *part = reinterpret_cast<Stat *>(p->B);                              // kPrepBlocks partials + 3 totals
+    static_assert(sizeof(Stat) * (kPrepBlocks + 3) <= kPrepScratchBytes, "prep scratch too small");
+    Stat *part = reinterpret_cast<Stat *>(p->prep_scratch);                   // kPrepBlocks partials + 3 totals
     Stat *tot = part + kPrepBlocks;
     { LaunchScope ls(p, KC_OTHER, s);
       tmpl_pass1_kernel<<<kPrepBlocks, 256, 0, s>>>(tmpl, mask, p->nz, p->ny, p->nx, laplace, work, part); }

@@ -5,10 +5,11 @@ Mirrors /root/reference/src/powerfit_em/powerfitter.py:50-92: the caller sets
 arrays), optionally ``_queues`` / ``_nproc`` / ``directory``, calls ``scan()`` and
 reads ``_lcc`` / ``_rot``.  Here ``scan()`` always runs the CUDA correlator (the
 reference's ``_gpu_scan``, :83-92); ``_queues`` may carry CUDA device ordinals, and
-``_nproc`` is accepted but ignored -- there is no CPU path in this package.  Under an
-initialised ``torch.distributed`` process group the rotation list is sharded over the
-ranks exactly like ``_cpu_scan`` shards it over processes (:95-108) and merged on the
-device instead of through ``.npy`` files (:146-163).
+``_nproc`` is accepted but ignored -- there is no CPU path in this package.  With
+``shard=True`` (opt-in; every rank of the process group must then run the same search) the
+rotation list is sharded over the ranks of an initialised ``torch.distributed`` group
+exactly like ``_cpu_scan`` shards it over processes (:95-108) and merged on the device
+instead of through ``.npy`` files (:146-163).
 """
 from os.path import abspath, isdir
 
@@ -23,8 +24,10 @@ def _array_of(obj):
 
 class PowerFitter(object):
 
-    def __init__(self, target, laplace=False):
+    def __init__(self, target, laplace=False, shard=False, group=None):
         self._target = target
+        self._shard = shard
+        self._group = group
         self._rotations = None
         self._template = None
         self._mask = None
@@ -55,7 +58,8 @@ class PowerFitter(object):
             q = self._queues[0]
             device = q if isinstance(q, (int, str)) or hasattr(q, "type") else None
         self._corr = CUDACorrelator(_array_of(self._target), device=device, laplace=self._laplace,
-                                    batch=self._batch, pad=self.pad_to_fused)
+                                    batch=self._batch, pad=self.pad_to_fused, shard=self._shard,
+                                    group=self._group)
         self._corr.template = _array_of(self._template)
         self._corr.mask = _array_of(self._mask)
         self._corr.rotations = self._rotations

@@ -34,8 +34,11 @@ def lower_resolution(array, voxelspacing, res_high, res_low, device=None):
     import torch
     lib = _lib.load()
     sigma_k = np.sqrt(res_to_sigma(res_low) ** 2 - res_to_sigma(res_high) ** 2) / voxelspacing
-    w, radius = _gaussian_weights(sigma_k)
     a = np.ascontiguousarray(array, dtype=np.float64)
+    if sigma_k <= 1e-15:
+        # scipy.ndimage.gaussian_filter skips axes with sigma <= 1e-15: the map comes back unchanged
+        return a.copy()
+    w, radius = _gaussian_weights(sigma_k)
     dev = _device(device)
     nz, ny, nx = a.shape
     with torch.cuda.device(dev):

@@ -159,20 +159,26 @@ def test_contract_errors(pfb):
 
 
 def test_perfect_fit_gives_unit_lcc(pfb):
-    """reference tests/test_powerfitter.py:67-79 through the whole CUDA chain."""
-    g = load_golden("lcc_chain")
-    shape = (6, 10, 8)
+    """reference tests/test_powerfitter.py:67-79 through the whole CUDA chain: a template equal to the map,
+    an all-ones mask and the identity rotation score LCC = 1 at voxel 0 and nowhere higher.  (The reference
+    test bypasses the rotation; here the map lives inside the rmax sphere so that the rotation keeps all of it.)"""
+    shape = (10, 12, 14)
     rng = np.random.default_rng(5)
-    target = rng.random(shape)
+    r = np.array(np.meshgrid(*[np.minimum(np.arange(n), n - np.arange(n)) for n in shape], indexing="ij"))
+    inside = (r ** 2).sum(0) <= (min(shape) // 2) ** 2 - 1
+    target = np.where(inside, rng.random(shape) + 0.5, 0.0)
     c = pfb.CUDACorrelator(target)
     c._lcc_mask[:] = 1
-    import torch
     c._d_lcc_mask.fill_(1)
+    import ctypes
+    from powerfit_b200 import _lib
+    _lib.check(c._libh.pfb_set_target(c._plan, c._d_target.data_ptr(), c._d_lcc_mask.data_ptr(), c._stream()))
     c.template = target.copy()
-    c.mask = np.ones(shape)
-    # rmax sphere would crop the template; widen nothing -- instead compare to the oracle
+    c.mask = inside.astype(np.float64)
     c.rotations = np.eye(3)
     c.scan()
+    assert abs(float(c.lcc[0, 0, 0]) - 1.0) < 1e-5, c.lcc[0, 0, 0]
+    assert int(np.argmax(c.lcc)) == 0 and c.rot[0, 0, 0] == 0
     assert c.lcc.max() <= 1 + 1e-5
 
 
@@ -223,6 +229,72 @@ def test_scan_128_subset_golden(pfb, name):
     target, template, mask = golden_inputs(g, name)
     c = run_scan(pfb, target, template, mask, g["rotations"], bool(g["laplace"]))
     check_against_golden(c, g)
+
+
+def solutions_agree(rows, want, top, tol=LCC_TOL):
+    """north_star acceptance rule for solutions.out: the top-N solutions have identical positions and rotations.
+    Rows whose scores differ by less than the LCC tolerance may swap ranks, so every reference row is looked up
+    by position; its rotation matrix must be identical and its score within the tolerance."""
+    rows, want = np.asarray(rows, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    got = {tuple(r[3:6]): r for r in rows}
+    for k, w in enumerate(want[:top]):
+        assert tuple(w[3:6]) in got, (k, w[:6])
+        r = got[tuple(w[3:6])]
+        assert abs(r[0] - w[0]) <= tol, (k, r[0], w[0])
+        assert np.array_equal(r[6:], w[6:]), (k, r[6:], w[6:])
+    # same order wherever neighbouring reference scores are further apart than the tolerance
+    n = min(top, len(want), len(rows))
+    for k in range(n):
+        lo_ok = k == 0 or want[k - 1][0] - want[k][0] > 2 * tol
+        hi_ok = k + 1 >= len(want) or want[k][0] - want[k + 1][0] > 2 * tol
+        if lo_ok and hi_ok:
+            assert tuple(rows[k][3:6]) == tuple(want[k][3:6]), (k, rows[k][:6], want[k][:6])
+
+
+def test_gpu_scan_to_solutions_config1(pfb):
+    """GPU scan -> Analyzer against reference scan -> reference Analyzer (BASELINE config 1, all 648 rotations):
+    solutions.out has the same positions and rotations (tests/golden/make_golden_analyzer.py)."""
+    from test_oracle import analyzer_case
+    from powerfit_b200.analyzer import Analyzer
+    g = load_golden("scan_config1_64")
+    target, template, mask = golden_inputs(g, "scan_config1_64")
+    c = run_scan(pfb, target, template, mask, g["rotations"], False)
+    lcc, rot, rotations, steps, vs, origin, zs, positions, solutions, text = analyzer_case("scan_config1_64")
+    a = Analyzer(c.lcc, rotations, c.rot, steps=steps, voxelspacing=vs, origin=origin, z_sigma=zs)
+    solutions_agree(a.solutions, solutions, top=min(100, len(solutions)))
+
+
+def test_scan_config2_full_golden(pfb, tmp_path):
+    """BASELINE configs[1] in full: 128^3, Laplace, the whole 10 degree set (7416 rotations), against the
+    reference CPU path run in the build container (tests/golden/make_golden_full128.py): LCC within 1e-4 and
+    rotation index identical where decided on the stored z planes, the global maximum, and solutions.out --
+    GPU scan -> Analyzer against reference scan -> reference Analyzer."""
+    from powerfit_b200.analyzer import Analyzer
+    g = load_golden("scan_config2_128_full")
+    target, template, mask = golden_inputs(g, "scan_config2_128_full")
+    c = run_scan(pfb, target, template, mask, g["rotations"], True)
+    assert float(c._norm_factor) == float(g["norm_factor"])
+    planes = g["planes"]
+    lcc, rot = c.lcc[planes], c.rot[planes]
+    err = np.abs(lcc - g["lcc"]).max()
+    assert err <= LCC_TOL, err
+    decided = (g["lcc"] - g["lcc2"]) > LCC_TOL
+    assert decided.sum() > 1000
+    assert np.array_equal(rot[decided], g["rot"][decided])
+    lm = np.unpackbits(g["lcc_mask"])[:lcc.size].reshape(lcc.shape).astype(bool)
+    assert (lcc[~lm] == 0).all() and (rot[~lm] == 0).all()
+    assert tuple(np.unravel_index(np.argmax(c.lcc), c.lcc.shape)) == tuple(int(v) for v in g["argmax"])
+    assert abs(float(c.lcc.max()) - float(g["lcc64_max"])) <= LCC_TOL
+    assert abs(float(c.lcc.astype(np.float64).sum()) - float(g["lcc_sum"])) <= 1e-5 * float(g["lcc_sum"])
+    steps, vs, ox, oy, oz, zs = (float(v) for v in g["analyzer_params"])
+    a = Analyzer(c.lcc, g["rotations"], c.rot, steps=int(steps), voxelspacing=vs, origin=(ox, oy, oz), z_sigma=zs)
+    solutions_agree(a.solutions, g["solutions"], top=min(100, len(g["solutions"])))
+    out = tmp_path / "solutions.out"
+    a.tofile(str(out))
+    got, want = out.read_text().splitlines(), str(g["solutions_text"]).splitlines()
+    assert got[0] == want[0]
+    print("config2 full: max |dLCC| = %.3g, %d solutions (reference %d), identical text rows: %d of %d"
+          % (err, len(a.solutions), len(g["solutions"]), sum(x == y for x, y in zip(got, want)), len(want)))
 
 
 def test_shards_merge_to_single_pass(pfb):
@@ -309,6 +381,45 @@ def test_several_templates_on_one_correlator(pfb):
         shared.scan()
         fresh = run_scan(pfb, case.target, tmpl, mask, rots, True)
         assert np.array_equal(shared.lcc, fresh.lcc) and np.array_equal(shared.rot, fresh.rot)
+
+
+def test_multi_template_slots_equal_fresh_correlators(pfb, oracle):
+    """BASELINE configs[4] (a batch of distinct templates against one map): MultiTemplateCorrelator keeps one
+    template slot per sub-unit on ONE plan (shared FT(map), FT(map^2), work buffers) and scan_all() gives, for every
+    template, exactly what a fresh single-template correlator gives -- on a fused grid and on an any-shape grid,
+    where it is also checked against the oracle."""
+    from powerfit_b200 import MultiTemplateCorrelator, synth
+    for shape, laplace in (((64, 64, 64), True), ((20, 24, 18), False)):
+        kw = dict(shape=shape, voxelspacing=3.0, resolution=9.0)
+        big = shape[0] >= 64
+        cases = [synth.make_case(n_res=120 if big else 30, rg=12.0 if big else 6.0, n_copies=3, seed=41, **kw),
+                 synth.make_case(n_res=70 if big else 20, rg=9.0 if big else 5.0, n_copies=1, seed=42, core_weighted=True, **kw),
+                 synth.make_case(n_res=40 if big else 12, rg=7.0 if big else 4.0, n_copies=1, seed=43, **kw)]
+        target = cases[0].target
+        rots = synth.random_rotations(11, seed=8)
+        m = MultiTemplateCorrelator(target, len(cases), laplace=laplace)
+        for i in (2, 0, 1):                                           # any filling order
+            m.set_template(i, cases[i].template, cases[i].mask)
+        m.rotations = rots
+        m.scan_all()
+        assert m.last_scan_rotations == len(cases) * len(rots)
+        for i, cs in enumerate(cases):
+            fresh = run_scan(pfb, target, cs.template, cs.mask, rots, laplace)
+            assert np.array_equal(m.lccs[i], fresh.lcc) and np.array_equal(m.rots[i], fresh.rot), i
+            if not big:
+                o = oracle.OracleCorrelator(target, laplace=laplace)
+                o.template, o.mask, o.rotations = cs.template, cs.mask, rots
+                o.scan(track_second=True)
+                ref = np.nan_to_num(o.lcc)
+                assert np.abs(m.lccs[i] - ref).max() <= LCC_TOL
+                decided = (ref - o._lcc2) > LCC_TOL
+                assert np.array_equal(m.rots[i][decided], o.rot[decided].astype(np.int32))
+        # a slot stays valid after others were used: the plain single-template call on the selected slot
+        m.select(1)
+        m.scan()
+        assert np.array_equal(m.lcc, m.lccs[1]) and np.array_equal(m.rot, m.rots[1])
+        with pytest.raises(ValueError):
+            m.select(len(cases))
 
 
 def test_padding_to_a_fused_cube(pfb):
@@ -552,14 +663,13 @@ dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%(port)d", rank=ran
 from powerfit_b200 import CUDACorrelator
 g = np.load(os.path.join(%(root)r, "tests", "golden", "scan_32_plain.npz"))
 target, template, mask = (g[k].astype(np.float64) for k in ("target", "template", "mask"))
-c = CUDACorrelator(target, device=rank)
+c = CUDACorrelator(target, device=rank, shard=True)
 c.template, c.mask, c.rotations = template, mask, g["rotations"]
 c.scan()                                   # shards the rotation list, merges with one MAX all-reduce
 ok = np.abs(c.lcc - g["lcc"]).max() <= 1e-4
 decided = (g["lcc"] - g["lcc2"]) > 1e-4
 ok = ok and np.array_equal(c.rot[decided], g["rot"][decided])
-single = CUDACorrelator(target, device=rank)
-single.shard = False
+single = CUDACorrelator(target, device=rank)         # shard=False: the whole list on this rank
 single.template, single.mask, single.rotations = template, mask, g["rotations"]
 single.scan()
 ok = ok and np.array_equal(single.lcc, c.lcc) and np.array_equal(single.rot, c.rot)

@@ -199,3 +199,19 @@ def test_target_prep_host_steps_match_reference():
     assert e.shape == (16, 20, 15) and np.count_nonzero(e) == np.count_nonzero(sub) and np.array_equal(e[:14, :18, :14], sub)
     with pytest.raises(ValueError, match="Cutoff value should be lower than density max."):
         T.trim(r, vs, [0, 0, 0], r.max())
+
+
+def test_template_work_items_cover_every_rotation_once():
+    """(template, rotation block) items of the multi-template search: every (template, rotation) exactly once,
+    blocks contiguous like powerfitter.py:95-108, and the same number of items on every rank."""
+    from powerfit_b200 import template_work_items
+    for T, nrot, world in [(4, 207576, 8), (4, 1000, 2), (4, 7416, 1), (3, 101, 4), (1, 648, 8), (5, 50, 3), (4, 10, 8)]:
+        items = template_work_items(T, nrot, world)
+        assert len(items) % world == 0
+        per_rank = [len(items[r::world]) for r in range(world)]
+        assert len(set(per_rank)) == 1
+        seen = np.zeros((T, nrot), dtype=np.int64)
+        for t, lo, hi in items:
+            assert 0 <= lo <= hi <= nrot
+            seen[t, lo:hi] += 1
+        assert (seen == 1).all()

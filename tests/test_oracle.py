@@ -230,3 +230,25 @@ def test_oracle_pyramid_matches_reference(oracle):
         assert np.array_equal(low, g["low_%d" % i])
         out, nvs = oracle.resample(low, vs, vs / (float(res) / 4.0))
         assert np.array_equal(out, g["res_%d" % i]) and nvs == float(g["vs_%d" % i])
+
+
+def test_oracle_reproduces_full_search_maximum(oracle):
+    """Headline-size pin (BASELINE configs[1], 128^3, Laplace, all 7416 rotations of the 10 degree set, run by
+    the REAL reference: tests/golden/make_golden_full128.py).  The oracle recomputes the one rotation that wins
+    at the global maximum and must reproduce the reference's LCC there; solutions.out's first row is that voxel."""
+    from conftest import golden_inputs
+    g = load_golden("scan_config2_128_full")
+    assert g["rotations"].shape == (7416, 3, 3)
+    target, template, mask = golden_inputs(g, "scan_config2_128_full")
+    top = g["solutions"][0]
+    steps, vs, ox, oy, oz, zs = (float(v) for v in g["analyzer_params"])
+    z, y, x = (int(v) for v in g["argmax"])
+    assert np.allclose(top[3:6], [x * vs + ox, y * vs + oy, z * vs + oz], rtol=0, atol=1e-9)
+    assert abs(top[0] - float(g["lcc64_max"])) < 1e-12
+    hits = [i for i, R in enumerate(g["rotations"]) if np.array_equal(R.ravel(), top[6:])]
+    assert hits
+    o = oracle.OracleCorrelator(target, laplace=True)
+    o.template, o.mask, o.rotations = template, mask, g["rotations"][hits[:1]]
+    o.scan()
+    assert float(o._norm_factor) == float(g["norm_factor"])
+    assert abs(float(o.lcc[z, y, x]) - float(g["lcc64_max"])) < 1e-9
