@@ -137,6 +137,9 @@ struct Plan {
     uint32_t *mbits = nullptr;                     // lcc_mask bit-packed in kernel C's lane layout
     CUtensorMap tmapC;                             // kernel C's view of the X2 work buffer (tma.cuh)
     const void *tmapC_base = nullptr;              // buffer the map was encoded for
+    CUtensorMap tmapB;                             // kernel B's view of the X1 work buffer (staging copies)
+    const void *tmapB_base = nullptr;
+    int tmapB_rs = -1, tmapB_nsig = -1;
     int rs = 0, rs2 = 0;
     unsigned ymask = 0;
     // class-decimated variant of kernels B and C (fused_cls.cu)

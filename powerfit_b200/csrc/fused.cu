@@ -165,12 +165,18 @@ template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8,
 // (tmem.cuh) before multiplying, and the ave2 plane has no phase 1 and no forward z: its phase 2 fetches the
 // parked spectrum, multiplies by FT(map^2) and transforms back.  That removes one of three forward (y,z)
 // transforms from the shared-memory pipe.
-template <int N, int THREADS>
+//
+// STAGED: the support rows of the next forward plane do not come straight from global memory inside the row loop
+// (an L2 round trip per row that 16 resident warps cannot hide: 11 % of the stall samples,
+// profiles/r02_ncu_v1_fused_full.txt) but are copied by TMA -- two 3-D boxes, rows z = 0..rs and z = N-rs..N-1 of
+// the (pair, signal, kx) plane of X1, issued by one thread while phase 2 runs -- into a staging area behind the
+// plane, and the row loop reads them from shared memory.  Used when the staging area fits (2 rs + 2 rows).
+template <int N, int THREADS, bool STAGED>
 __global__ void __launch_bounds__(THREADS, FusedCfg<N>::CTAS)
 fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fpk,
                        const float4 *__restrict__ F2pk, const float2 *__restrict__ twN_g,
                        const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g, int rs,
-                       unsigned ymask, int nsig, int npairs) {
+                       unsigned ymask, int nsig, int npairs, const __grid_constant__ CUtensorMap tmapX1) {
     using Cfg = FusedCfg<N>;
     constexpr int H = N / 2, P = H + 1;
     constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
@@ -185,6 +191,9 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     float2 *twM = twN + N;                                        // [EM][LM] W_H^(t k1)
     float2 *twh_s = twM + H;                                      // [H] W_N^k of the split radix-2 step
     uint32_t *tslot = reinterpret_cast<uint32_t *>(twh_s + H);
+    uint64_t *sbar = reinterpret_cast<uint64_t *>(tslot + 2);                          // staging copies have landed
+    // staging rows: zi = z for z <= rs, zi = rs + 1 + (z - (N - rs)) for the rows below zero; 128-byte aligned
+    float4 *stage = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(sbar + 1) + 112);
     const size_t slab = (size_t)N * H;                                                 // float4 per z
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // LM = 4: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo the
@@ -201,6 +210,19 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
     for (int i = threadIdx.x; i < H; i += THREADS) { twM[i] = twM_g[i]; twh_s[i] = twh_g[i]; }
     if (warp == 0) tmem_alloc(tslot, TCOLS);
+    // one thread: both boxes of plane (j, v) of X1 -> staging area
+    auto stage_issue = [&](int j, int v) {
+        const int pair = j % npairs, kx = j / npairs;
+        mbar_arrive_expect_tx(sbar, (uint32_t)(2 * (rs + 1) * H * sizeof(float4)));
+        tma_load_4d(stage, &tmapX1, sbar, 0, kx, 0, pair * nsig + v);
+        tma_load_4d(stage + (rs + 1) * H, &tmapX1, sbar, 0, kx, N - rs, pair * nsig + v);   // last row out of bounds: zeros
+    };
+    if (STAGED && threadIdx.x == 0) {
+        mbar_init(sbar, 1);
+        mbar_fence_init();
+        if (job < njobs) stage_issue(job, 0);
+    }
+    uint32_t sphase = 0;
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
@@ -228,6 +250,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
                 const int pair = cjob % npairs, kx = cjob / npairs;
                 dst = X2 + (size_t)(pair * 3 + cvol) * N * slab + (size_t)kx * H;      // + z*slab + y/2
             }
+            if (STAGED && fwd) { mbar_wait(sbar, sphase); sphase ^= 1u; }
             for (int w = warp; w < N / GM; w += NW) {
                 const int z = w * GM + gM;
                 const bool act = fwd && (z + rs) % N < nzv;
@@ -245,7 +268,13 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) {
                         const int jj = tM + LM * n1;                                   // y = 2jj, 2jj+1
-                        vn[n1] = (act && ((ymask >> (jj >> 4)) & 1u)) ? ldg_c2(src + (size_t)z * slab + jj) : c2_zero();
+                        const bool have = act && ((ymask >> (jj >> 4)) & 1u);
+                        if (STAGED) {
+                            const int zi = z <= rs ? z : z - (N - rs) + rs + 1;
+                            vn[n1] = have ? lds_c2(stage + zi * H + jj) : c2_zero();
+                        } else {
+                            vn[n1] = have ? ldg_c2(src + (size_t)z * slab + jj) : c2_zero();
+                        }
                     }
                     // a pencil group outside the support box rides along without touching shared memory
                     fft_row_adj2split<LM, EM>(vn, plane + z * P, 1, tM, tw, twh, act);
@@ -259,19 +288,28 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
         __syncthreads();
         if (job >= njobs) break;
 
-        // pull the support rows of the CTA's next forward plane towards L2 while phase 2 runs (one 128-byte
-        // line per thread): the row loop's direct loads then see L2 instead of HBM latency
+        // the CTA's next forward plane: copy its support rows into the staging area (STAGED), or pull them towards
+        // L2 (one 128-byte line per thread), while phase 2 runs
         {
             int jn = job, vn = vol + 1;
             if (vn == 3 || (binary && vn == 2)) { vn = 0; jn += gridDim.x; }
-            const int nlines = nzv * 2 * __popc(ymask);
-            if (jn < njobs && (int)threadIdx.x < nlines) {
-                const int pair = jn % npairs, kx = jn / npairs;
-                const int j = threadIdx.x / (2 * __popc(ymask)), l = threadIdx.x % (2 * __popc(ymask));
-                const int z = (j - rs + N) % N, tile = __fns(ymask, 0, (l >> 1) + 1);
-                const float4 *a = X1 + (size_t)(pair * nsig + vn) * N * slab + (size_t)kx * H + (size_t)z * slab +
-                                  16 * tile + 8 * (l & 1);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            if (STAGED) {
+                // (a plane without phase 1 -- ave2 of a binary mask -- changes nothing: its successor's rows were
+                // staged during the previous phase 2 and are still waiting)
+                if (threadIdx.x == 0 && jn < njobs && fwd) {
+                    fence_proxy_async_smem();
+                    stage_issue(jn, vn);
+                }
+            } else {
+                const int nlines = nzv * 2 * __popc(ymask);
+                if (jn < njobs && (int)threadIdx.x < nlines) {
+                    const int pair = jn % npairs, kx = jn / npairs;
+                    const int j = threadIdx.x / (2 * __popc(ymask)), l = threadIdx.x % (2 * __popc(ymask));
+                    const int z = (j - rs + N) % N, tile = __fns(ymask, 0, (l >> 1) + 1);
+                    const float4 *a = X1 + (size_t)(pair * nsig + vn) * N * slab + (size_t)kx * H + (size_t)z * slab +
+                                      16 * tile + 8 * (l & 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                }
             }
         }
 
@@ -572,8 +610,8 @@ fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint3
     }
 }
 
-int make_x2_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer,
-                       int box_floats, int box_kx) {
+static int encode_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer,
+                             const cuuint32_t (&box)[4], CUtensorMapSwizzle swizzle) {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -591,16 +629,27 @@ int make_x2_tensor_map(CUtensorMap *out, const void *base, int row_floats, int n
     const cuuint64_t dims[4] = {(cuuint64_t)row_floats, (cuuint64_t)nkx, (cuuint64_t)nz, (cuuint64_t)outer};
     const cuuint64_t strides[3] = {(cuuint64_t)row_floats * 4, (cuuint64_t)row_floats * 4 * nkx,
                                    (cuuint64_t)row_floats * 4 * nkx * nz};
-    const cuuint32_t box[4] = {(cuuint32_t)box_floats, (cuuint32_t)box_kx, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return PFB_ERR_CUDA;
     }
     return PFB_OK;
+}
+
+int make_x2_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer,
+                       int box_floats, int box_kx) {
+    const cuuint32_t box[4] = {(cuuint32_t)box_floats, (cuuint32_t)box_kx, 1, 1};
+    return encode_tensor_map(out, base, row_floats, nkx, nz, outer, box,
+                             box_floats * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+int make_x1_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer, int box_z) {
+    const cuuint32_t box[4] = {(cuuint32_t)row_floats, 1, (cuuint32_t)box_z, 1};
+    return encode_tensor_map(out, base, row_floats, nkx, nz, outer, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 // ------------------------------------------------------------------------------- helpers
@@ -660,9 +709,15 @@ __global__ void support_kernel(const float *__restrict__ tmpl, const float *__re
 }
 
 // ------------------------------------------------------------------------------- host side
-// plane + twiddle tables + the TMEM base address slot
-template <int N> static constexpr size_t smem_b() {
-    return (size_t)(N * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2) + 16;
+// plane + twiddle tables + the TMEM base address slot + the staging barrier (padded to a 128-byte boundary) +
+// `srows` staging rows of N/2 float4 (0 = unstaged kernel)
+template <int N> static constexpr size_t smem_b(int srows) {
+    return (size_t)(N * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2) + 128 +
+           (size_t)srows * (N / 2) * sizeof(float4);
+}
+// staging rows that fit next to the plane(s) of an SM
+template <int N> static constexpr int stage_capacity() {
+    return (int)((227 * 1024 / FusedCfg<N>::CTAS - 1024 - smem_b<N>(0)) / ((N / 2) * sizeof(float4)));
 }
 template <int N> static constexpr size_t smem_c(int rt) {
     return (size_t)N * (rt / 2 + 1) * sizeof(float4) + (size_t)rt * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
@@ -695,8 +750,10 @@ template <int N> static int fused_init_n(Plan *p) {
     constexpr int TP = 33;
     PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256)>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<N>(0)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<N>(stage_capacity<N>())));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_c<N>(16)));
     PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -790,12 +847,28 @@ int launch_fused_a(Plan *p, int first, int count, cudaStream_t s) {
 template <int N, int BT>
 static int fused_b_n(Plan *p, int count, float2 *X2, cudaStream_t s) {
     const int npairs = (count + 1) / 2;
-    LaunchScope ls(p, KC_FUSED_B, s);
     const int njobs = N * npairs;
-    fused_fftyz_mul_kernel<N, BT><<<std::min(njobs, p->sm_count * FusedCfg<N>::CTAS), BT, smem_b<N>(), s>>>(
-        reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
-        reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
-        p->tw[0], p->rs, p->ymask, p->nsig, npairs);
+    const int grid = std::min(njobs, p->sm_count * FusedCfg<N>::CTAS);
+    static const bool stage_env = getenv("PFB_B_STAGE") ? atoi(getenv("PFB_B_STAGE")) != 0 : true;
+    const int srows = 2 * p->rs + 2;
+    const bool staged = stage_env && 2 * p->rs + 1 < N && srows <= stage_capacity<N>();
+    if (staged && (p->tmapB_base != (const void *)p->A || p->tmapB_rs != p->rs || p->tmapB_nsig != p->nsig)) {
+        // X1 as [pair*nsig+sig][z][kx][2N floats]; box = one whole (z, kx) row x (rs + 1) consecutive z
+        int rc = make_x1_tensor_map(&p->tmapB, p->A, 2 * N, N, N, (long)p->nsig * (p->batch / 2), p->rs + 1);
+        if (rc) return rc;
+        p->tmapB_base = p->A; p->tmapB_rs = p->rs; p->tmapB_nsig = p->nsig;
+    }
+    LaunchScope ls(p, KC_FUSED_B, s);
+    if (staged)
+        fused_fftyz_mul_kernel<N, BT, true><<<grid, BT, smem_b<N>(srows), s>>>(
+            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
+            reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
+            p->tw[0], p->rs, p->ymask, p->nsig, npairs, p->tmapB);
+    else
+        fused_fftyz_mul_kernel<N, BT, false><<<grid, BT, smem_b<N>(0), s>>>(
+            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
+            reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
+            p->tw[0], p->rs, p->ymask, p->nsig, npairs, p->tmapB);
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }

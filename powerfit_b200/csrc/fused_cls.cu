@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "rotate_device.cuh"
+#include "tmem.cuh"
+#include "tma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -165,26 +167,34 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
 }
 
 // ------------------------------------------------------------------------------- kernel B
-// Plane q = ((kx * 3 + volume) * npairs + pair) * NB + b; the grid is a multiple of NB, so a
-// persistent CTA keeps its class b = blockIdx.x % NB for all its planes and neighbouring CTAs
-// share the input rows (b fastest) and the map-spectrum tile (pair next).
+// Job j = (kx * npairs + pair) * NB + b, the three output planes gcc, ave, ave2 of one (kx, pair, class) in a row;
+// the grid is a multiple of NB, so a persistent CTA keeps its class b = blockIdx.x % NB for all its jobs and
+// neighbouring CTAs share the input rows (b fastest) and the map-spectrum tile (pair next).
+// Binary mask with 8-lane column pencils (N = 192): as in fused_fftyz_mul_kernel, the forward spectrum of the mask
+// is computed once, parked in tensor memory (tmem.cuh) and fetched back for the ave2 plane, which then has no
+// phase 1 and no forward z.
 // Tile layout: plane[z][c], c < 32, float4 = columns (k' = c, c + 32) in split form.
 template <int N>
 __global__ void __launch_bounds__(ClsCfg<N>::THREADS, ClsCfg<N>::CTAS)
 cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fc,
                      const float4 *__restrict__ F2c, const float2 *__restrict__ twN_g,
                      const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g,
-                     int rs, unsigned nmask, int nsig, int nplanes) {
+                     int rs, unsigned nmask, int nsig, int npairs) {
     using Cfg = ClsCfg<N>;
     constexpr int H = N / 2, HC = 32, P = 33, NB = Cfg::NB, PPT = Cfg::PPT;
     constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
     constexpr int LM = 4, EM = 8, GM = 8;                        // row pencils: packed 32 points (64-point rows)
     constexpr int THREADS = Cfg::THREADS, NW = THREADS / 32;
+    constexpr bool STASH = LN == 8;                              // the TMEM helpers move 8 packed pairs at a time
+    constexpr int CIT = HC / GN / NW;                            // column groups per warp
+    constexpr uint32_t TCOLS = 256;                              // CIT * 4 EN columns per lane, rounded up to a power of two
+    static_assert(!STASH || (NW <= 4 && CIT * 4 * EN <= (int)TCOLS && TCOLS * Cfg::CTAS <= 512), "TMEM stash geometry");
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                        // [N][P]
     float2 *twN = reinterpret_cast<float2 *>(plane + N * P);      // [EN][LN] W_N^(t k1)
     float2 *twM = twN + N;                                        // [EM][LM] W_32^(t k1)
     float2 *twh_s = twM + 32;                                     // [32] W_64^k of the split radix-2 step
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(twh_s + 32);
     const size_t slab = (size_t)N * H;                            // float4 per z of X1 / X2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // row pencils: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo
@@ -192,44 +202,54 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
     const int tM = lane & 3, gM = (lane >> 3) + 4 * ((lane >> 2) & 1);
     const int tN = lane & (LN - 1), gN = lane / LN;
     const int nzv = min(2 * rs + 1, N);
-    const int npairs = nplanes / (3 * N * NB);
+    const int njobs = N * npairs * NB;
     const int b = blockIdx.x % NB;
+    const bool stash = STASH && nsig == 2;
 
-    int q = blockIdx.x;          // plane whose phase 1 comes next
-    int qcur = -1;               // plane whose phase 2 is done (phase 3 pending)
+    int job = blockIdx.x, vol = 0;      // plane whose phase 1 comes next
+    int cjob = -1, cvol = 0;            // plane whose phase 2 is done (phase 3 pending)
     for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
     for (int i = threadIdx.x; i < 32; i += THREADS) {
         twM[i] = twM_g[i];
         twh_s[i] = twh_g[i];
     }
+    uint32_t tcol = 0;
+    if (STASH) {
+        if (warp == 0) tmem_alloc(tslot, TCOLS);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        tcol = *tslot + ((uint32_t)(32 * warp) << 16);           // NW <= 4: every warp its own lane quarter
+    }
 
     while (true) {
-        __syncthreads();          // phase 2 of plane qcur is complete (first pass: the tables are in place)
+        __syncthreads();          // phase 2 of the current plane is complete (first pass: the tables are in place)
+        const bool fwd = job < njobs && !(stash && vol == 2);
         {
-            // ---- row loop: phase 3 of plane qcur (inverse y of the class, shared -> HBM), then phase 1
-            //      of plane q (forward y of the folded rows inside the support box, HBM -> shared)
+            // ---- row loop: phase 3 of plane (cjob, cvol) (inverse y of the class, shared -> HBM), then phase 1
+            //      of plane (job, vol) (forward y of the folded rows inside the support box, HBM -> shared)
             float2 twr[EM], twh[EM];
 #pragma unroll
             for (int m = 0; m < EM; ++m) { twr[m] = twM[m * LM + tM]; twh[m] = twh_s[tM + LM * m]; }
             const TwReg<EM> tw{twr};
             const float4 *src = X1;
-            if (q < nplanes) {
-                const int qq = q / NB;
-                const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
+            if (fwd) {
+                const int jj = job / NB;
+                const int pair = jj % npairs, kx = jj / npairs;
                 const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
                 src = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H + b * 32;   // + z*slab + n/2
             }
             float4 *dst = X2;
-            if (qcur >= 0) {
-                const int qq = qcur / NB;
-                const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
-                dst = X2 + (size_t)(pair * 3 + vol) * N * slab + (size_t)kx * H;       // + z*slab + tile offset
+            if (cjob >= 0) {
+                const int jj = cjob / NB;
+                const int pair = jj % npairs, kx = jj / npairs;
+                dst = X2 + (size_t)(pair * 3 + cvol) * N * slab + (size_t)kx * H;      // + z*slab + tile offset
             }
             for (int w = warp; w < N / GM; w += NW) {
                 const int z = w * GM + gM;
-                const bool act = q < nplanes && (z + rs) % N < nzv;
+                const bool act = fwd && (z + rs) % N < nzv;
                 const bool any = __any_sync(0xffffffffu, act);
-                if (qcur >= 0) {
+                if (cjob >= 0) {
                     C2 v[EM];
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) v[n1] = lds_c2(plane + z * P + tM + LM * n1);
@@ -258,16 +278,17 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
             }
         }
         __syncthreads();
-        if (q >= nplanes) break;
+        if (job >= njobs) break;
 
-        // pull the support rows of the CTA's next plane towards L2 while phase 2 runs (512 bytes per row and
-        // class): the row loop's direct loads then see L2 instead of HBM latency
+        // pull the support rows of the CTA's next forward plane towards L2 while phase 2 runs (512 bytes per row
+        // and class): the row loop's direct loads then see L2 instead of HBM latency
         {
-            const int qn = q + gridDim.x;
-            if (qn < nplanes) {
-                const int qq = qn / NB;
-                const int pair = qq % npairs, vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
-                const int sig = vol == 0 ? 0 : (vol == 1 ? 1 : nsig - 1);
+            int jn = job, vn = vol + 1;
+            if (vn == 3 || (stash && vn == 2)) { vn = 0; jn += gridDim.x; }
+            if (jn < njobs) {
+                const int jj = jn / NB;
+                const int pair = jj % npairs, kx = jj / npairs;
+                const int sig = vn == 0 ? 0 : (vn == 1 ? 1 : nsig - 1);
                 const float4 *nxt = X1 + (size_t)(pair * nsig + sig) * N * slab + (size_t)kx * H + b * 32;
                 for (int i = threadIdx.x; i < 4 * nzv; i += THREADS) {
                     const int z = ((i >> 2) - rs + N) % N;
@@ -278,28 +299,44 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 
         // ---- phase 2: forward z, multiply with the map spectrum, inverse z (column pairs k', k' + 32)
         {
-            const int qq = q / NB;
-            const int vol = (qq / npairs) % 3, kx = qq / (3 * npairs);
+            const int kx = job / NB / npairs;
             const float4 *Fm = (vol == 2 ? F2c : Fc) + (size_t)(kx * NB + b) * HC * N;   // + c*N + kz
             const TwSmem<LN> tw{twN + tN};
-            for (int w = warp; w < HC / GN; w += NW) {
-                const int c = w * GN + gN;
+#pragma unroll 1
+            for (int it = 0; it < CIT; ++it) {
+                const int c = (warp + it * NW) * GN + gN;
                 C2 v[EN];
+                if (fwd) {
 #pragma unroll
-                for (int n1 = 0; n1 < EN; ++n1) {
-                    const int z = tN + LN * n1;
-                    const int sz = z <= N / 2 ? z : z - N;
-                    v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + c) : c2_zero();
+                    for (int n1 = 0; n1 < EN; ++n1) {
+                        const int z = tN + LN * n1;
+                        const int sz = z <= N / 2 ? z : z - N;
+                        v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + c) : c2_zero();
+                    }
                 }
-                if (LN >= 16 && THREADS > 256) fft_pencil2_mul_late<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
-                else fft_pencil2_mul<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
+                if constexpr (STASH) {
+                    if (fwd) {
+                        fft_pencil2_mul_stash<false, LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN,
+                                                             tcol + it * 4 * EN, stash && vol == 1);
+                        tmem_wait_st();
+                    } else {
+                        fft_pencil2_mul_stash<true, LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN,
+                                                            tcol + it * 4 * EN, false);
+                    }
+                } else {
+                    if (LN >= 16 && THREADS > 256) fft_pencil2_mul_late<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
+                    else fft_pencil2_mul<LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN);
+                }
                 fft_pencil2<LN, EN>(v, plane + c, P, tN, tw);
 #pragma unroll
                 for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + c, v[m]);
             }
         }
-        qcur = q;
-        q += gridDim.x;
+        cjob = job; cvol = vol;
+        if (++vol == 3) { vol = 0; job += gridDim.x; }
+    }
+    if (STASH) {
+        if (warp == 0) tmem_dealloc(*tslot, TCOLS);
     }
 }
 
@@ -437,6 +474,219 @@ cls_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------- kernel C, TMA-fed
+// Same work split as cls_ifftx_lcc_kernel, three changes (measured reasons in DESIGN.md):
+//  * the tile arrives as tensor-map boxes (tma.cuh) issued by one thread -- at N = 256 one 128-byte-wide box
+//    (NB PPT = 8 float4 per kx) in the 128-byte swizzle, at N = 192 one 64-byte-wide box per class in the
+//    64-byte swizzle -- so the dense rows need no padding to be conflict free and no thread spends registers or
+//    issue slots on 16-byte cp.async copies;
+//  * 1/sqrt(var) of a thread's 2 rows x E x-values x 2 rotations (64 / 96 registers at N = 256 / 192) waits in
+//    tensor memory between the ave2, ave and gcc tiles of a rotation pair instead of in registers (tmem.cuh:
+//    the same thread stores and fetches, no layout involved): the old kernel needed 255 registers at N = 192;
+//  * the running best of the chunk is kept as float LCC + 16-bit rotation offset (6 instead of 8 bytes per
+//    voxel), which lets a third CTA fit next to the tiles.
+template <int N> struct ClsC {
+    using Cfg = ClsCfg<N>;
+    static constexpr int NB = Cfg::NB, PPT = Cfg::PPT, NPC = NB * PPT, L = Cfg::LC, E = N / L, Q = E / L;
+    static constexpr int W4 = NPC * 16 <= 128 ? NPC : PPT;        // float4 per row of one TMA box
+    static constexpr int NBOX = NPC / W4;
+    static constexpr int THREADS = NPC * L, RT = 2 * NPC, BP = N + 4, TILE = N * NPC, CTAS = 3;
+    static constexpr uint32_t TCOLS = 4 * E <= 64 ? 64 : 128;      // TMEM columns per CTA: 4 E per lane, every warp its own lane quarter
+    static_assert(W4 == 8 || W4 == 4, "128-byte or 64-byte swizzle");
+    static_assert(THREADS <= 128, "at most four warps: one TMEM lane quarter each");
+    // XOR pattern of the swizzle for a row whose low bits are k (plus the row's own offset bits below the box row stride)
+    __host__ __device__ static constexpr int xc(int k) { return W4 == 8 ? (8 * (k & (L - 1)) | (k & 7)) : (4 * (k & 7) | ((k >> 1) & 3)); }
+    static constexpr size_t smem() {
+        return 1024 + (size_t)TILE * sizeof(float4) + (size_t)RT * BP * (sizeof(float) + sizeof(uint16_t)) + (size_t)N * sizeof(float2) +
+               sizeof(uint64_t) + 16;
+    }
+};
+
+template <int N>
+__global__ void __launch_bounds__(ClsC<N>::THREADS, ClsC<N>::CTAS)
+cls_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ mbits,
+                         const float4 *__restrict__ fold_g, float norm, int first_index, int count,
+                         int pairs_per_chunk, int64_t *__restrict__ best, const float2 *__restrict__ twN_g) {
+    using G = ClsC<N>;
+    constexpr int L = G::L, E = G::E, NB = G::NB, PPT = G::PPT, NPC = G::NPC, W4 = G::W4, NBOX = G::NBOX;
+    constexpr int RT = G::RT, BP = G::BP, THREADS = G::THREADS, Q = G::Q, TILE = G::TILE, RS = W4 * L;   // RS: float4 per L rows of a box
+    extern __shared__ uint8_t smem_raw[];
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));   // [NBOX][N][W4]
+    float *lb_lcc = reinterpret_cast<float *>(tile + TILE);           // [RT][BP] best LCC of the chunk
+    float2 *tws = reinterpret_cast<float2 *>(lb_lcc + RT * BP);       // [E][L] W_N^(t k1)
+    uint64_t *full = reinterpret_cast<uint64_t *>(tws + N);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(full + 1);
+    uint16_t *lb_rot = reinterpret_cast<uint16_t *>(tslot + 2);       // [RT][BP] its rotation, relative to the chunk's first
+    const int u = blockIdx.x, z = blockIdx.y;
+    const int npairs = (count + 1) / 2;
+    const int p0 = blockIdx.z * pairs_per_chunk, p1 = min(npairs, p0 + pairs_per_chunk);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & (L - 1), pc = (32 / L) * warp + lane / L;    // pencil = tile slot pc = (class, pair)
+    const int ya = 2 * (u * PPT + pc % PPT) + 64 * (pc / PPT);        // rows ya, ya + 1
+    const size_t rowa = ((size_t)z * N + ya) * N, rowb = rowa + N;
+    float *la = lb_lcc + (2 * pc) * BP + t, *lb = la + BP;
+    uint16_t *ra = lb_rot + (2 * pc) * BP + t, *rb = ra + BP;
+    // bit m of a row's word t: lcc_mask at x = t + L m
+    const unsigned ma = mbits[((size_t)z * N + ya) * L + t], mb = mbits[((size_t)z * N + ya + 1) * L + t];
+    // swizzled position of this thread's pencil: box, column c inside the box row, u0 = offset of row t
+    const int box = pc / W4, c = pc % W4;
+    const int u0 = box * (N * W4) + W4 * t + (c ^ (W4 == 8 ? (t & 7) : ((t >> 1) & 3)));
+    const int nitems = 3 * (p1 - p0);
+    auto issue = [&](int item) {                                      // thread 0 only
+        const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
+        mbar_arrive_expect_tx(full, TILE * (uint32_t)sizeof(float4));
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx)
+            tma_load_4d(tile + bx * (N * W4), &tmap, full, 4 * (u * NPC + bx * W4), 0, z, p * 3 + vol);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        mbar_fence_init();
+        if (nitems > 0) issue(0);
+    }
+    if (warp == 0) tmem_alloc(tslot, G::TCOLS);
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        la[L * m] = 0.f; lb[L * m] = 0.f;
+        ra[L * m] = 0; rb[L * m] = 0;
+    }
+    for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = twN_g[i];
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tcol = *tslot + ((uint32_t)(32 * warp) << 16);
+    const TwSmem<L> tw{tws + t};
+    // class twiddles of this thread's column of the combine pass: W_N^(n' b), W_N^((n'+1) b)
+    const int cpp = W4 == 8 ? threadIdx.x / (THREADS / PPT) : threadIdx.x % PPT;
+    C2 twc[NB - 1];
+#pragma unroll
+    for (int bb = 1; bb < NB; ++bb) twc[bb - 1] = c2_from(__ldg(fold_g + bb * 32 + u * PPT + cpp));
+    const uint32_t rot0 = (uint32_t)(first_index + 2 * p0);
+    for (int item = 0; item < nitems; ++item) {
+        mbar_wait(full, (uint32_t)item & 1u);
+        // ---- class butterfly, in place: slot (b, p) -> slot (j, p) = rows n' + 64 j, n' + 64 j + 1
+        if (W4 == 8) {
+            // eight consecutive kx per quarter warp, one pair p: the swizzle spreads them over the eight 16-byte lanes
+            for (int row = threadIdx.x % (THREADS / PPT); row < N; row += THREADS / PPT) {
+                float4 *e = tile + row * 8;
+                C2 g[NB];
+#pragma unroll
+                for (int bb = 0; bb < NB; ++bb) g[bb] = lds_c2(e + ((bb * PPT + cpp) ^ (row & 7)));
+#pragma unroll
+                for (int bb = 1; bb < NB; ++bb) g[bb] = cmul(g[bb], twc[bb - 1]);
+                if (NB == 3) dft3(g[0], g[1], g[NB - 1]);
+                else dft4(g[0], g[1], g[2], g[NB - 1]);
+#pragma unroll
+                for (int bb = 0; bb < NB; ++bb) sts_c2(e + ((bb * PPT + cpp) ^ (row & 7)), g[bb]);
+            }
+        } else {
+            for (int row = threadIdx.x / PPT; row < N; row += THREADS / PPT) {
+                float4 *e = tile + row * 4 + (cpp ^ ((row >> 1) & 3));
+                C2 g[NB];
+#pragma unroll
+                for (int bb = 0; bb < NB; ++bb) g[bb] = lds_c2(e + bb * (N * 4));
+#pragma unroll
+                for (int bb = 1; bb < NB; ++bb) g[bb] = cmul(g[bb], twc[bb - 1]);
+                if (NB == 3) dft3(g[0], g[1], g[NB - 1]);
+                else dft4(g[0], g[1], g[2], g[NB - 1]);
+#pragma unroll
+                for (int bb = 0; bb < NB; ++bb) sts_c2(e + bb * (N * 4), g[bb]);
+            }
+        }
+        __syncthreads();
+        const int p = p0 + item / 3, vi = item % 3;
+        const uint32_t ia = (uint32_t)(first_index + 2 * p);
+        const bool have_b = 2 * p + 1 < count;
+        auto run_item = [&](auto vi_tag) {
+            constexpr int VI = decltype(vi_tag)::value;
+            {
+                C2 v[E];
+#pragma unroll
+                for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + RS * n1 + u0);
+                DftReg<E, C2>::run(v);
+#pragma unroll
+                for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
+                __syncwarp();
+#pragma unroll
+                for (int k1 = 0; k1 < E; ++k1) sts_c2(tile + RS * k1 + (u0 ^ G::xc(k1 & (L - 1))), v[k1]);
+                __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                C2 a[L];
+#pragma unroll
+                for (int n0 = 0; n0 < L; ++n0) a[n0] = lds_c2(tile + RS * L * q + RS * t + (u0 ^ G::xc(n0)));
+                DftReg<L, C2>::run(a);
+                if (q == Q - 1) {
+                    __syncthreads();       // every pencil is out of the tile: hand it back to the copy engine
+                    if (threadIdx.x == 0 && item + 1 < nitems) {
+                        fence_proxy_async_smem();
+                        issue(item + 1);
+                    }
+                }
+                // 1/sqrt(var) of output m = q + Q k0 lives in TMEM columns 4 (L q + k0) .. + 3 of this lane
+#pragma unroll
+                for (int h = 0; h < L / 8; ++h) {
+                    const uint32_t tc = tcol + 4 * (L * q + 8 * h);
+                    C2 sd[8];
+                    if (VI == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) sd[k] = a[8 * h + k];                  // ave2
+                        tmem_st_c2x8(tc, sd);
+                    } else {
+                        tmem_ld_c2x8(tc, sd);
+                        if (VI == 1) {                                                     // 1/sqrt(N ave2 - ave^2)
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const C2 av = a[8 * h + k];
+                                const float2 vr = psub(pmul(sd[k].re, pdup(norm)), pmul(av.re, av.re));
+                                const float2 vq = psub(pmul(sd[k].im, pdup(norm)), pmul(av.im, av.im));
+                                sd[k].re = make_float2(rsqrtf(vr.x), rsqrtf(vr.y));
+                                sd[k].im = make_float2(rsqrtf(vq.x), rsqrtf(vq.y));
+                            }
+                            tmem_st_c2x8(tc, sd);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int m = q + Q * (8 * h + k);
+                                const C2 gv = a[8 * h + k];
+                                const float2 va = pmul(gv.re, sd[k].re), vb = pmul(gv.im, sd[k].im);
+                                const bool sa = have_b && (vb.x > va.x || !(va.x == va.x));
+                                const bool sb = have_b && (vb.y > va.y || !(va.y == va.y));
+                                const float ca = sa ? vb.x : va.x, cb = sb ? vb.y : va.y;          // NaN never passes '>'
+                                const uint16_t ja = (uint16_t)(ia - rot0 + (sa ? 1u : 0u)), jb = (uint16_t)(ia - rot0 + (sb ? 1u : 0u));
+                                if (((ma >> m) & 1u) && ca > la[L * m]) { la[L * m] = ca; ra[L * m] = ja; }
+                                if (((mb >> m) & 1u) && cb > lb[L * m]) { lb[L * m] = cb; rb[L * m] = jb; }
+                            }
+                        }
+                    }
+                }
+            }
+            if (VI != 2) tmem_wait_st();
+        };
+        if (vi == 0) run_item(std::integral_constant<int, 0>{});
+        else if (vi == 1) run_item(std::integral_constant<int, 1>{});
+        else run_item(std::integral_constant<int, 2>{});
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        if ((ma >> m) & 1u) {
+            const float bv = la[L * m];
+            if (bv > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowa + t + L * m),
+                          (long long)pack_best(__float_as_uint(bv), rot0 + ra[L * m]));
+        }
+        if ((mb >> m) & 1u) {
+            const float bv = lb[L * m];
+            if (bv > 0.f)
+                atomicMax(reinterpret_cast<long long *>(best + rowb + t + L * m),
+                          (long long)pack_best(__float_as_uint(bv), rot0 + rb[L * m]));
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(*tslot, G::TCOLS);
+}
+
 // ------------------------------------------------------------------------------- helpers
 // Fc[kx][b][c][kz] = (re F[kz][ky0][kx], re F[kz][ky1][kx], im .., im ..), ky0 = NB c + b,
 // ky1 = NB (c + 32) + b: the map spectrum in kernel B's class / column-pair order
@@ -471,7 +721,7 @@ template <int N> static constexpr size_t smem_a_cls() {
     return (size_t)2 * N * (ClsCfg<N>::RN * (N / 64) + 1) * sizeof(float2);
 }
 template <int N> static constexpr size_t smem_b_cls() {
-    return (size_t)N * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2);
+    return (size_t)N * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2) + 16;
 }
 template <int N> static constexpr size_t smem_c_cls() {
     using Cfg = ClsCfg<N>;
@@ -521,6 +771,8 @@ template <int N> static int cls_init_n(Plan *p) {
                                   (int)smem_a_cls<N>()));
     PFB_CUDA(cudaFuncSetAttribute(cls_ifftx_lcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_c_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_ifftx_lcc_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ClsC<N>::smem()));
     return PFB_OK;
 }
 
@@ -550,15 +802,15 @@ int cls_prepare_target(Plan *p, cudaStream_t s) {
 template <int N> static int cls_b_n(Plan *p, int count, float2 *X2, cudaStream_t s) {
     using Cfg = ClsCfg<N>;
     const int npairs = (count + 1) / 2;
-    const int nplanes = N * 3 * npairs * Cfg::NB;
+    const int njobs = N * npairs * Cfg::NB;
     int grid = p->sm_count * Cfg::CTAS;
     grid -= grid % Cfg::NB;
-    grid = std::min(grid, nplanes);
+    grid = std::min(grid, njobs);
     LaunchScope ls(p, KC_FUSED_B, s);
     cls_fftyz_mul_kernel<N><<<grid, Cfg::THREADS, smem_b_cls<N>(), s>>>(
         reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
         reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->cls_twN, p->cls_twM,
-        p->cls_twh, p->rs, p->nmask, p->nsig, nplanes);
+        p->cls_twh, p->rs, p->nmask, p->nsig, npairs);
     return PFB_OK;
 }
 
@@ -568,11 +820,34 @@ template <int N> static int cls_c_n(Plan *p, int first, int count, int rot_index
     constexpr int NPC = Cfg::NB * Cfg::PPT;
     const int npairs = (count + 1) / 2;
     const int tiles = (N / 2 / NPC) * N;
-    int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * Cfg::CCTAS + tiles - 1) / tiles));
-    int ppc = (npairs + chunks - 1) / chunks;
+    static const bool tma_env = getenv("PFB_CLS_C_TMA") ? atoi(getenv("PFB_CLS_C_TMA")) != 0 : true;
+    const int per_sm = tma_env ? ClsC<N>::CTAS : Cfg::CCTAS;
+    // whole waves of resident CTAs, at least 4 pairs per CTA (see fused_back_tma in fused.cu)
+    const int slots = p->sm_count * per_sm;
+    int ppc = std::max(1, npairs);
+    double best_eff = -1.0;
+    for (int cand = std::min(npairs, 32); cand >= std::min(npairs, 4); --cand) {
+        const double waves = (double)tiles * ((npairs + cand - 1) / cand) / slots;
+        const double eff = waves / std::ceil(waves);
+        if (waves >= 3.0 && eff > best_eff + 1e-9) { best_eff = eff; ppc = cand; }
+    }
+    if (best_eff < 0) ppc = std::max(1, std::min(npairs, 4));
     static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
     if (ppc_env > 0) ppc = ppc_env;
-    chunks = (npairs + ppc - 1) / ppc;
+    ppc = std::min(ppc, 32000);                   // 16-bit rotation offsets inside a chunk
+    const int chunks = (npairs + ppc - 1) / ppc;
+    if (tma_env) {
+        if (p->tmapC_base != (const void *)X2) {
+            // X2 as [pair*3+vol][z][kx][2N floats]; box = W4 float4 x all kx (W4 = a tile row, or one class of it)
+            int rc = make_x2_tensor_map(&p->tmapC, X2, 2 * N, N, N, 3L * (p->batch / 2), 4 * ClsC<N>::W4, N);
+            if (rc) return rc;
+            p->tmapC_base = X2;
+        }
+        LaunchScope ls(p, KC_FUSED_C, s);
+        cls_ifftx_lcc_tma_kernel<N><<<dim3(N / 2 / NPC, N, chunks), ClsC<N>::THREADS, ClsC<N>::smem(), s>>>(
+            p->tmapC, p->mbits, p->cls_fold, p->norm_factor, rot_index_offset + first, count, ppc, best, p->cls_twN);
+        return PFB_OK;
+    }
     LaunchScope ls(p, KC_FUSED_C, s);
     cls_ifftx_lcc_kernel<N><<<dim3(N / 2 / NPC, N, chunks), NPC * Cfg::LC, smem_c_cls<N>(), s>>>(
         reinterpret_cast<const float4 *>(X2), p->mbits, p->cls_fold, p->norm_factor, rot_index_offset + first, count,

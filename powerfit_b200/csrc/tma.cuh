@@ -50,8 +50,11 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *t
 }
 
 // Host: tensor map of a work buffer laid out [outer][z][kx][row_floats] float32, box = box_floats x box_kx x 1 x 1,
-// 128-byte swizzle.  The driver entry point is looked up at run time so that the library does not link libcuda.
+// 128-byte swizzle for 128-byte box rows, 64-byte swizzle for 64-byte ones.  The driver entry point is looked up at run time so that the library does not link libcuda.
 int make_x2_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer,
                        int box_floats, int box_kx);
+// Host: the same 4-D view of the work buffer X1, box = one whole row x 1 kx x box_z consecutive z, no swizzle
+// (kernel B's staging copies).
+int make_x1_tensor_map(CUtensorMap *out, const void *base, int row_floats, int nkx, int nz, long outer, int box_z);
 
 }  // namespace pfb

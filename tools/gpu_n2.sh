@@ -1,11 +1,16 @@
 #!/bin/bash
-# 2-GPU check: the driver's launch line for both arms (ours, reference) at N=2, and the reference arm at N=1
+# N GPUs (default 2): the 2-GPU NCCL parity test, then the driver's torchrun bench line (merge_check + strong inside)
+N=${1:-2}
 mkdir -p gpurun_out
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_n1.json 2> gpurun_out/ref_err.txt
-cat gpurun_out/bench_reference_n1.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/n2_err.txt
-cat gpurun_out/bench_n2.json; tail -5 gpurun_out/n2_err.txt
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-    bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_reference_n2.json 2>> gpurun_out/ref_err.txt
-cat gpurun_out/bench_reference_n2.json; tail -5 gpurun_out/ref_err.txt
+nvidia-smi -L | head -8
+timeout 900 python -m pytest tests -m gpu -q -x -k "two_gpu" 2>&1 | tail -3
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/n${N}_err.txt
+tail -3 gpurun_out/n${N}_err.txt
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_n$N.json'))
+print('N=%d rot/s %.0f e2e %.0f frac %.3f' % (d['n_gpus'], d['value'], d['e2e']['value'], d['roofline']['step_frac']))
+print('merge_check', d.get('merge_check'))
+print('strong', d.get('strong'))
+PY
