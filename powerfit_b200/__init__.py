@@ -9,6 +9,6 @@ from ._lib import PowerfitB200Error, build, load  # noqa: F401
 from .correlator import CUDACorrelator, MultiTemplateCorrelator, shard_bounds, template_work_items  # noqa: F401
 from .powerfitter import PowerFitter  # noqa: F401
 from .analyzer import Analyzer  # noqa: F401
-from . import shapes, pyramid, target_prep  # noqa: F401
+from . import shapes, pyramid, target_prep, volume_io  # noqa: F401
 
 __version__ = "0.1.0"

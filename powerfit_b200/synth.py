@@ -111,6 +111,19 @@ def core_weight(mask):
     return depth
 
 
+def make_template(shape, voxelspacing, resolution, n_res, rg, seed, core_weighted=False):
+    """Template density and mask of a seeded random-walk model, centred on voxel 0 (what make_case builds)."""
+    shape = tuple(shape)
+    xyz = random_walk_trace(n_res, rg, seed)
+    sigma_vox = max(resolution / (np.sqrt(2.0) * np.pi) / voxelspacing, 0.6)
+    xv = xyz / voxelspacing
+    template = splat_gaussians(xv, sigma_vox, shape)
+    mask = splat_balls(xv, max(5.0 / voxelspacing, 1.5), shape)
+    if core_weighted:
+        mask = core_weight(mask)
+    return template, mask
+
+
 def make_case(n=64, voxelspacing=2.0, resolution=8.0, n_res=300, rg=14.0, n_copies=3,
               seed=0, noise=0.05, core_weighted=False, shape=None, name=""):
     """A map with ``n_copies`` posed copies of a random-walk model, and the model's

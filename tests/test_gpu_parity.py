@@ -723,3 +723,25 @@ def test_target_prep_matches_reference_golden(pfb):
     assert np.abs(arr - ref).max() <= 4 * np.finfo(np.float64).eps * np.abs(ref).max()
     cube, _, _ = T.prepare_target(g["map"], float(g["voxelspacing"]), list(g["origin"]), float(g["resolution"]), fused=True)
     assert cube.shape == (64, 64, 64) and np.array_equal(cube[:ref.shape[0], :ref.shape[1], :ref.shape[2]], arr)
+
+
+def test_map_file_to_search(pfb, tmp_path):
+    """N3 end to end: a map written as .mrc is read back into page-locked memory (volume_io.read_map_f32), and the
+    search on the Volume read from the file equals the search on the array that was written (float32 map)."""
+    import torch
+    from powerfit_b200 import synth, volume_io as V
+    case = synth.make_case(n=32, voxelspacing=3.0, resolution=9.0, n_res=60, rg=8.0, n_copies=2, seed=77)
+    target = case.target.astype(np.float32)
+    path = str(tmp_path / "map.mrc")
+    V.Volume(target, 3.0, (1.5, -3.0, 6.0)).tofile(path)
+    a, vs, origin, m = V.read_map_f32(path)
+    assert m._pin is not None and m._pin.is_pinned() and a.dtype == np.float32
+    assert np.array_equal(a, target) and abs(vs - 3.0) < 1e-6 and list(origin) == [1.5, -3.0, 6.0]
+    vol = V.Volume.fromfile(path)
+    rots = synth.random_rotations(6, seed=4)
+    c1 = run_scan(pfb, vol.array, case.template, case.mask, rots, True)
+    c2 = run_scan(pfb, target.astype(np.float64), case.template, case.mask, rots, True)
+    assert np.array_equal(c1.lcc, c2.lcc) and np.array_equal(c1.rot, c2.rot)
+    V.Volume(c1.lcc, vs, origin).tofile(str(tmp_path / "lcc.mrc"))               # powerfit.py:306-308
+    back, _, _ = V.parse_volume(str(tmp_path / "lcc.mrc"))
+    assert np.array_equal(back.astype(np.float32), c1.lcc)

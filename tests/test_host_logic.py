@@ -215,3 +215,77 @@ def test_template_work_items_cover_every_rotation_once():
             assert 0 <= lo <= hi <= nrot
             seen[t, lo:hi] += 1
         assert (seen == 1).all()
+
+
+def test_volume_io_matches_reference_files(tmp_path):
+    """N3 file IO: CCP4 / MRC files written by the real reference (tests/golden/make_golden_volume_io.py) parse
+    to exactly what the reference's parser returns, and our writer produces the reference's bytes."""
+    from powerfit_b200 import volume_io as V
+    g = load_golden("volume_io")
+    for name in g["names"]:
+        name = str(name)
+        ext = str(g[name + "_ext"])
+        raw = g[name + "_bytes"].tobytes()
+        path = tmp_path / (name + "." + ext)
+        path.write_bytes(raw)
+        dens, vs, origin = V.parse_volume(str(path))
+        want = g[name + "_density"]
+        assert dens.dtype == want.dtype and np.array_equal(dens, want), name
+        assert vs == float(g[name + "_voxelspacing"]) and np.array_equal(np.asarray(origin, dtype=np.float64), g[name + "_origin"])
+        with open(path, "rb") as fh:                          # an open file works for every extension here
+            d2, vs2, o2 = V.parse_volume(fh)
+        assert np.array_equal(d2, want) and vs2 == vs
+        vol = V.Volume.fromfile(str(path))
+        assert vol.shape == want.shape and np.array_equal(vol.array, want)
+        # writer: same bytes as the reference wrote from the same array
+        meta = g[name + "_meta"]
+        out = tmp_path / ("out_" + name + "." + ext)
+        V.Volume(g[name + "_array"], float(meta[0]), tuple(float(v) for v in meta[1:])).tofile(str(out))
+        assert out.read_bytes() == raw, name
+        # float32 block for the GPU upload
+        a, vs3, o3, _ = V.read_map_f32(str(path))
+        assert a.dtype == np.float32 and np.array_equal(a, want.astype(np.float32)) and vs3 == vs
+    # big-endian file: same values
+    name = "f64_mrc"
+    raw = bytearray(g[name + "_bytes"].tobytes())
+    head = np.frombuffer(bytes(raw[:1024]), dtype=V._header_dtype("<"))[0]
+    be = np.zeros(1, dtype=V._header_dtype(">"))[0]
+    for k in head.dtype.names:
+        be[k] = head[k]
+    hb = bytearray(be.tobytes())
+    hb[208:216] = b"MAP \x11\x11\x00\x00"
+    data = np.frombuffer(bytes(raw[1024:]), dtype="<f4").astype(">f4").tobytes()
+    p = tmp_path / "be.mrc"
+    p.write_bytes(bytes(hb) + data)
+    dens, vs, origin = V.parse_volume(str(p))
+    assert np.array_equal(dens, g[name + "_density"]) and vs == float(g[name + "_voxelspacing"])
+
+
+def test_volume_io_errors(tmp_path):
+    """The reference's refusals: unknown extension, bad machine stamp, skewed cell, unequal spacing."""
+    from powerfit_b200 import volume_io as V
+    g = load_golden("volume_io")
+    raw = bytearray(g["f64_mrc_bytes"].tobytes())
+    with pytest.raises(ValueError, match="Extension of file is not supported"):
+        V.parse_volume(str(tmp_path / "x.txt"))
+    bad = bytearray(raw); bad[212] = 0x00
+    (tmp_path / "stamp.mrc").write_bytes(bytes(bad))
+    with pytest.raises(RuntimeError, match="Endiannes"):
+        V.parse_volume(str(tmp_path / "stamp.mrc"))
+    import struct
+    bad = bytearray(raw); bad[52:56] = struct.pack("<f", 80.0)            # alpha
+    (tmp_path / "skew.mrc").write_bytes(bytes(bad))
+    with pytest.raises(RuntimeError, match="rectangular"):
+        V.parse_volume(str(tmp_path / "skew.mrc"))
+    bad = bytearray(raw); bad[40:44] = struct.pack("<f", 99.0)            # xlength
+    (tmp_path / "spacing.mrc").write_bytes(bytes(bad))
+    with pytest.raises(RuntimeError, match="Voxel spacing"):
+        V.parse_volume(str(tmp_path / "spacing.mrc"))
+    bad = bytearray(raw); bad[64:68] = struct.pack("<i", 2); bad[68:72] = struct.pack("<i", 1)    # mapc, mapr swapped
+    (tmp_path / "order.mrc").write_bytes(bytes(bad))
+    with pytest.raises(RuntimeError, match="axis order"):
+        V.parse_volume(str(tmp_path / "order.mrc"))
+    with pytest.raises(TypeError):
+        V.to_mrc(str(tmp_path / "c.mrc"), V.Volume(np.zeros((2, 2, 2), dtype=np.complex64)))
+    with pytest.raises(RuntimeError, match="Format is not supported"):
+        V.Volume(np.zeros((2, 2, 2))).tofile(str(tmp_path / "c.xplor"))
