@@ -365,14 +365,19 @@ class CUDACorrelator(object):
             if world > 1:
                 dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
             ev[2].record(stream)
-            lcc = torch.empty(self._shape, dtype=torch.float32, device=self._device)
-            rot = torch.empty(self._shape, dtype=torch.int32, device=self._device)
+            # both grids in one device buffer -> ONE DMA transfer into page-locked host memory (powerfitter.py:536-537)
+            V = int(np.prod(self._shape))
+            out = torch.empty(2 * V, dtype=torch.int32, device=self._device)
+            lcc, rot = out[:V].view(torch.float32), out[V:]
             _lib.check(self._libh.pfb_unpack(self._plan, best.data_ptr(), lcc.data_ptr(), rot.data_ptr(),
                                              self._stream()))
-            self._lcc = lcc.cpu().numpy()             # powerfitter.py:536-537
-            self._rot = rot.cpu().numpy()
+            host, h = self._result_buffer(2 * V)
+            host.copy_(out, non_blocking=True)
             ev[3].record(stream)
             ev[3].synchronize()
+            self._lcc = h[:V].view(np.float32).reshape(self._shape)
+            self._rot = h[V:].reshape(self._shape)
+            del h
             if self._crop is not None:
                 nz, ny, nx = self._crop
                 self._lcc = np.ascontiguousarray(self._lcc[:nz, :ny, :nx])
@@ -381,6 +386,22 @@ class CUDACorrelator(object):
         self.last_scan_profile = {"rotations": int(hi - lo), "world": int(world),
                                   "search_ms": ev[0].elapsed_time(ev[1]), "allreduce_ms": ev[1].elapsed_time(ev[2]),
                                   "unpack_download_ms": ev[2].elapsed_time(ev[3])}
+
+    def _result_buffer(self, count):
+        """Page-locked int32 host buffer for the result grids, as (tensor, numpy base array).  `.lcc` / `.rot` are
+        views of the base array, so the buffer of the previous scan is reused only when nothing outside this object
+        still refers to it (the caller may have kept the earlier arrays, or views of them, the way it can keep the
+        fresh arrays the reference returns); otherwise a new buffer is allocated."""
+        import sys
+        torch = self._torch
+        prev = getattr(self, "_host_result", None)
+        if prev is not None and prev[0].numel() == count:
+            self._lcc = self._rot = None
+            if sys.getrefcount(prev[1]) <= 2:          # the tuple's reference + the call argument: no view is alive
+                return prev
+        t = torch.empty(count, dtype=torch.int32).pin_memory()
+        self._host_result = (t, t.numpy())
+        return self._host_result
 
     @staticmethod
     def _print_progress(n, nrot, time0):               # powerfitter.py:540-547
