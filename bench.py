@@ -79,7 +79,7 @@ def search_rotations(workload, count):
 def default_batch(n):
     """pfb_plan_create's default rotations per batch (csrc/api.cu)."""
     per_pair = 6 * n ** 3 * 8
-    pairs = max(1, min(256 if per_pair <= (32 << 20) else 128, (24576 << 20) // per_pair))
+    pairs = max(1, min(256, (32768 << 20) // per_pair))
     return 2 * pairs
 
 

@@ -196,6 +196,14 @@ int pfb_gaussian_filter(const double *in, double *out, double *tmp, int nz, int 
  * interpolation onto an oz*oy*ox grid, x_in = x_out (n_in - 1) / (n_out - 1). */
 int pfb_zoom_linear(const double *in, int nz, int ny, int nx, double *out, int oz, int oy, int ox, void *stream);
 
+/* Test hook: one FFT building block of the fused kernels (csrc/fft_core.cuh) on caller data, so that each of them
+ * can be pinned against a reference FFT on its own -- the role clFFT's own test-suite plays for the reference's
+ * grfftn_builder plans (powerfitter.py:605-638).  in/out: DEVICE float4[count][lanes*e].
+ * kind 0: packed pencil (two independent complex sequences per element, lanes*e points);
+ * kind 1 / 2: row transforms of ONE sequence of 2*lanes*e points, adjacent-in -> split-out / split-in -> adjacent-out;
+ * kind 3: scalar pencil (lanes = 8).  Kernel exp(+2 pi i n k / N), un-normalised. */
+int pfb_pencil_fft(int kind, int lanes, int e, const float *in, float *out, int count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ SYMBOLS = ["pfb_version", "pfb_last_error", "pfb_plan_create", "pfb_plan_destroy
            "pfb_merge_best", "pfb_profile", "pfb_profile_read", "pfb_rotate", "pfb_fft3_c2c", "pfb_lcc_take_best", "pfb_search_host",
            "pfb_lcc_max", "pfb_peak_candidates", "pfb_prepare_target", "pfb_prepare_template",
            "pfb_blur_points", "pfb_dilate_points", "pfb_core_indices",
-           "pfb_gaussian_filter", "pfb_zoom_linear", "pfb_template_slots", "pfb_select_template"]
+           "pfb_gaussian_filter", "pfb_zoom_linear", "pfb_template_slots", "pfb_select_template", "pfb_pencil_fft"]
 
 _lib = None
 
@@ -85,6 +85,7 @@ def load():
     lib.pfb_prepare_template.argtypes = [vp, vp, vp, i32, vp, vp, c.POINTER(c.c_double), c.POINTER(i32), vp]
     lib.pfb_template_slots.argtypes = [vp, i32]
     lib.pfb_select_template.argtypes = [vp, i32]
+    lib.pfb_pencil_fft.argtypes = [i32, i32, i32, vp, vp, i32, vp]
     lib.pfb_best_init.argtypes = [vp, vp, vp]
     lib.pfb_scan.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.pfb_unpack.argtypes = [vp, vp, vp, vp, vp]

@@ -541,12 +541,20 @@ class MultiTemplateCorrelator(CUDACorrelator):
                 done += hi - lo
             if world > 1:
                 dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
-            lcc = torch.empty((T,) + tuple(self._shape), dtype=torch.float32, device=self._device)
-            rot = torch.empty((T,) + tuple(self._shape), dtype=torch.int32, device=self._device)
+            # all grids in one device buffer -> one DMA transfer into page-locked host memory
+            out = torch.empty(2 * T * V, dtype=torch.int32, device=self._device)
+            d_lcc, d_rot = out[:T * V].view(torch.float32).view(T, V), out[T * V:].view(T, V)
             for t in range(T):
-                _lib.check(self._libh.pfb_unpack(self._plan, best[t].data_ptr(), lcc[t].data_ptr(), rot[t].data_ptr(),
-                                                 self._stream()))
-            lcc, rot = lcc.cpu().numpy(), rot.cpu().numpy()
+                _lib.check(self._libh.pfb_unpack(self._plan, best[t].data_ptr(), d_lcc[t].data_ptr(),
+                                                 d_rot[t].data_ptr(), self._stream()))
+            self.lccs = [None] * T
+            self.rots = [None] * T
+            host, h = self._result_buffer(2 * T * V)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(self._device).synchronize()
+            lcc = h[:T * V].view(np.float32).reshape((T,) + tuple(self._shape))
+            rot = h[T * V:].reshape((T,) + tuple(self._shape))
+            del h
         for t in range(T):
             self.lccs[t], self.rots[t] = lcc[t], rot[t]
             if self._crop is not None:

@@ -129,12 +129,12 @@ int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan 
     DeviceGuard guard(device);
     if (!guard.ok) { delete h; set_error("cudaSetDevice failed"); return PFB_ERR_CUDA; }
     if (max_batch <= 0) {
-        // default: as many rotations in flight as fit ~24 GB of work buffers (of 180 GB), 2..256 (2..512 for small grids).  Measured at
-        // 128^3: 64 -> 47.4k, 128 -> 48.5k, 256 -> 49.0k rotations/s; at 64^3: 64 -> 269k, 256 -> 298k (longer
-        // launches amortise tails, prologues and the per-CTA start-up of the persistent kernel)
+        // default: as many rotations in flight as fit ~32 GB of work buffers (of 180 GB), at most 512.  Measured at
+        // 128^3: 64 -> 47.4k, 128 -> 48.5k, 256 -> 54.3k, 512 -> 54.8k rotations/s; at 64^3: 64 -> 269k, 256 -> 298k,
+        // 512 -> 311k (longer launches amortise tails, prologues and the per-CTA start-up of the persistent kernel)
         const long per_pair = 6L * p->V * (long)sizeof(float2);
-        long pairs = (24576L << 20) / per_pair;
-        pairs = std::max(1L, std::min(per_pair <= (32L << 20) ? 256L : 128L, pairs));   // 64^3: 512 -> 311k
+        long pairs = (32768L << 20) / per_pair;
+        pairs = std::max(1L, std::min(256L, pairs));
         max_batch = (int)(2 * pairs);
     }
     if (const char *e = getenv("PFB_BATCH")) max_batch = std::max(1, atoi(e));

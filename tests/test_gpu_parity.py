@@ -99,6 +99,46 @@ def test_fft3_matches_numpy(pfb, shape):
     assert np.abs(out - ref).max() / scale < 2e-6
 
 
+@pytest.mark.parametrize("lanes,e", [(4, 8), (8, 8), (8, 16), (8, 24), (16, 16)])
+def test_fused_pencil_building_blocks_match_numpy(pfb, lanes, e):
+    """Operator-level pin of the register / shared-memory FFT blocks the fused kernels are made of
+    (csrc/fft_core.cuh through pfb_pencil_fft): packed pencils, both row transforms with the split radix-2 step,
+    and the scalar pencil, for every (lanes, points per lane) geometry the search uses, against numpy."""
+    import ctypes
+    import torch
+    from powerfit_b200 import _lib
+    lib = _lib.load()
+    n, count = lanes * e, 37                       # 37: a last, partly filled warp
+    rng = np.random.default_rng(lanes * 100 + e)
+    cplx = lambda *shape: rng.normal(size=shape) + 1j * rng.normal(size=shape)
+
+    def run(kind, packed):
+        d_in = torch.from_numpy(np.ascontiguousarray(packed, dtype=np.float32)).cuda()
+        d_out = torch.empty_like(d_in)
+        _lib.check(lib.pfb_pencil_fft(kind, lanes, e, d_in.data_ptr(), d_out.data_ptr(), count,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return d_out.cpu().numpy().astype(np.float64)
+
+    pack = lambda a, b: np.stack([a.real, b.real, a.imag, b.imag], axis=-1)        # C2 = (re0, re1, im0, im1)
+    unpack = lambda o: (o[..., 0] + 1j * o[..., 2], o[..., 1] + 1j * o[..., 3])
+    dft = lambda x: np.fft.ifft(x, axis=-1) * x.shape[-1]                          # exp(+2 pi i n k / N)
+    tol = lambda ref: 3e-6 * np.abs(ref).max()
+    # packed pencil: two independent sequences
+    a, b = cplx(count, n), cplx(count, n)
+    oa, ob = unpack(run(0, pack(a, b)))
+    assert np.abs(oa - dft(a)).max() < tol(dft(a)) and np.abs(ob - dft(b)).max() < tol(dft(b))
+    # row transforms of one 2n-point sequence
+    x = cplx(count, 2 * n)
+    X = dft(x)
+    lo, hi = unpack(run(1, pack(x[:, 0::2], x[:, 1::2])))                          # adjacent in -> (X[k], X[k+n])
+    assert np.abs(lo - X[:, :n]).max() < tol(X) and np.abs(hi - X[:, n:]).max() < tol(X)
+    ev, od = unpack(run(2, pack(x[:, :n], x[:, n:])))                              # split in -> (X[2k], X[2k+1])
+    assert np.abs(ev - X[:, 0::2]).max() < tol(X) and np.abs(od - X[:, 1::2]).max() < tol(X)
+    if lanes == 8 and e in (8, 16):                                                # kernel A's scalar pencil
+        o = run(3, np.stack([a.real, a.imag, 0 * a.real, 0 * a.real], axis=-1))    # scalar: float4 = (re, im, -, -)
+        assert np.abs(o[..., 0] + 1j * o[..., 1] - dft(a)).max() < tol(dft(a))
+
+
 def test_lcc_take_best_edge_cases(pfb, oracle):
     """calc_lcc + take-best: zero/negative variance, ties, negative LCC, mask off."""
     shape = (4, 4, 6)

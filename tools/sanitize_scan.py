@@ -1,4 +1,4 @@
-"""compute-sanitizer target: one small search per fused pipeline (64^3, 128^3, 256^3 class path) plus the
+"""compute-sanitizer target: one small search per fused pipeline (64^3, 128^3, 192^3 / 256^3 class path) plus the
 device preparation and shape kernels.  Run as: compute-sanitizer --tool memcheck python tools/sanitize_scan.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,7 @@ from powerfit_b200 import CUDACorrelator, shapes, synth
 sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256]
 for n in sizes:
     case = synth.make_case(n=n, voxelspacing=2.8, resolution=9.0, n_res=120, rg=11.0, n_copies=2, seed=3,
-                           core_weighted=(n != 128))
+                           core_weighted=(n not in (128, 192)))      # 128 / 192: binary mask -> TMEM spectrum stash
     c = CUDACorrelator(case.target, laplace=True, batch=4)
     c.template, c.mask, c.rotations = case.template, case.mask, synth.random_rotations(5, seed=2)
     c.scan()
