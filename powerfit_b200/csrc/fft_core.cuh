@@ -74,9 +74,13 @@ __device__ __forceinline__ C2 lds_c2(const float4 *p) {
                  : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
     return r;
 }
+// Stores name their four 32-bit halves: with two 64-bit operands ptxas assembled every stored quad with four MOVs
+// in ONE scratch quad -- 281 MOVs in kernel B (11 % of its instructions), each group waiting for the previous store
+// to release the quad (7 % of the stall samples, profiles/r02_ncu_v3_fused_full.txt) -- while with four 32-bit
+// operands it allocates the producing FADD2/FFMA2 results in place (35 MOVs).
 __device__ __forceinline__ void sts_c2(float4 *p, C2 v) {
-    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)),
-                 "l"(*reinterpret_cast<const u64_t *>(&v.re)), "l"(*reinterpret_cast<const u64_t *>(&v.im)) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(p)),
+                 "f"(v.re.x), "f"(v.re.y), "f"(v.im.x), "f"(v.im.y) : "memory");
 }
 __device__ __forceinline__ C2 ldg_c2(const float4 *p) {
     C2 r;
@@ -85,8 +89,8 @@ __device__ __forceinline__ C2 ldg_c2(const float4 *p) {
     return r;
 }
 __device__ __forceinline__ void stg_c2(float4 *p, C2 v) {
-    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(*reinterpret_cast<const u64_t *>(&v.re)),
-                 "l"(*reinterpret_cast<const u64_t *>(&v.im)) : "memory");
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.re.x), "f"(v.re.y), "f"(v.im.x), "f"(v.im.y)
+                 : "memory");
 }
 __device__ __forceinline__ C2 c2_zero() { C2 r; r.re = make_float2(0.f, 0.f); r.im = make_float2(0.f, 0.f); return r; }
 

@@ -14,7 +14,7 @@ for k,v in d.get('configs',{}).items(): print(k, v.get('value'), v.get('step_fra
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras --rot-per-step 512 > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fused_ -s 30 -c 3 -o gpurun_out/fused_full -f \
+ncu --set full --clock-control none --import-source on -k regex:fused_ -s 6 -c 3 -o gpurun_out/fused_full -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras --rot-per-step 512 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ls -la gpurun_out | tail -5
