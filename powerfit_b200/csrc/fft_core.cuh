@@ -301,10 +301,24 @@ __device__ __forceinline__ void load_twiddles(float2 (&tw)[E], const float2 *__r
 // (TwReg) where they fit, or this lane's column of a [k1][t] table in shared memory (TwSmem:
 // the lanes of a pencil read one contiguous 8*LANES-byte run, conflict free).
 template <int E> struct TwReg {
+    static constexpr bool paired = false;
     const float2 (&w)[E];
     __device__ __forceinline__ float2 operator()(int k1) const { return w[k1]; }
 };
+// this lane's column of a table stored in PAIRS, [k1 / 2][t] of float4 = (W^(t 2k), W^(t (2k+1))): one 16-byte
+// load fetches two twiddles (the shared-memory instruction queue, not its bandwidth, is what kernel B runs out of)
+template <int LANES> struct TwSmemPair {
+    static constexpr bool paired = true;
+    const float4 *p;      // &table[0][t]
+    __device__ __forceinline__ float4 pair(int k) const {
+        float4 r;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                     : "r"((unsigned)__cvta_generic_to_shared(p + k * LANES)));
+        return r;
+    }
+};
 template <int LANES> struct TwSmem {
+    static constexpr bool paired = false;
     const float2 *p;      // &table[0][t]
     __device__ __forceinline__ float2 operator()(int k1) const {
         float2 r;
@@ -327,8 +341,17 @@ __device__ __forceinline__ void pencil2_stage1(C2 (&v)[E], float4 *scratch, int 
                                                bool active = true) {
     static_assert(E % LANES == 0, "E must be a multiple of LANES");
     DftReg<E, C2>::run(v);
+    if constexpr (TW::paired) {
 #pragma unroll
-    for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
+        for (int k = 0; k < E / 2; ++k) {
+            const float4 w = tw.pair(k);
+            if (k > 0) v[2 * k] = cmulw(v[2 * k], make_float2(w.x, w.y));
+            v[2 * k + 1] = cmulw(v[2 * k + 1], make_float2(w.z, w.w));
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
+    }
     __syncwarp();
     if (active) {
 #pragma unroll

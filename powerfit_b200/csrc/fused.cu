@@ -207,7 +207,11 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 
     int job = blockIdx.x, vol = 0;      // plane whose phase 1 comes next
     int cjob = -1, cvol = 0;            // plane whose phase 2 is done (phase 3 pending)
-    for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
+    // column twiddles in pairs: twN[(k1 / 2) * LN + t] = (W^(t 2k), W^(t (2k+1))) as float4
+    for (int i = threadIdx.x; i < N; i += THREADS) {
+        const int k1 = i / LN, tt = i % LN;
+        twN[2 * ((k1 >> 1) * LN + tt) + (k1 & 1)] = twN_g[i];
+    }
     for (int i = threadIdx.x; i < H; i += THREADS) { twM[i] = twM_g[i]; twh_s[i] = twh_g[i]; }
     if (warp == 0) tmem_alloc(tslot, TCOLS);
     // one thread: both boxes of plane (j, v) of X1 -> staging area
@@ -317,7 +321,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
         {
             const int kx = job / npairs;
             const float4 *Fm = (vol == 2 ? F2pk : Fpk) + (size_t)kx * H * N;           // + ky*N + kz
-            const TwSmem<LN> tw{twN + tN};
+            const TwSmemPair<LN> tw{reinterpret_cast<const float4 *>(twN) + tN};
             const int ky = warp * GN + gN;
             C2 v[EN];
             if (fwd) {
