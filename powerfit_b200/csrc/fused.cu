@@ -528,9 +528,12 @@ fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint3
         lba[8 * m] = make_float2(0.f, 0.f);
         lbb[8 * m] = make_float2(0.f, 0.f);
     }
-    for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = twN_g[i];
+    for (int i = threadIdx.x; i < N; i += THREADS) {        // twiddles in pairs, as in kernel B
+        const int k1 = i / 8, tt = i % 8;
+        tws[2 * ((k1 >> 1) * 8 + tt) + (k1 & 1)] = twN_g[i];
+    }
     __syncthreads();
-    const TwSmem<8> tw{tws + t};
+    const TwSmemPair<8> tw{reinterpret_cast<const float4 *>(tws) + t};
     C2 sd[E];
     constexpr int Q = E / 8;
     for (int item = 0; item < nitems; ++item) {
@@ -548,7 +551,11 @@ fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint3
                 for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + 64 * n1 + u);
                 DftReg<E, C2>::run(v);
 #pragma unroll
-                for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
+                for (int k = 0; k < E / 2; ++k) {
+                    const float4 w = tw.pair(k);
+                    if (k > 0) v[2 * k] = cmulw(v[2 * k], make_float2(w.x, w.y));
+                    v[2 * k + 1] = cmulw(v[2 * k + 1], make_float2(w.z, w.w));
+                }
                 __syncwarp();
 #pragma unroll
                 for (int k1 = 0; k1 < E; ++k1) sts_c2(tile + 64 * k1 + (u ^ (9 * (k1 & 7))), v[k1]);

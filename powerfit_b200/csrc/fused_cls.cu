@@ -208,7 +208,10 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 
     int job = blockIdx.x, vol = 0;      // plane whose phase 1 comes next
     int cjob = -1, cvol = 0;            // plane whose phase 2 is done (phase 3 pending)
-    for (int i = threadIdx.x; i < N; i += THREADS) twN[i] = twN_g[i];
+    for (int i = threadIdx.x; i < N; i += THREADS) {        // column twiddles in pairs (fft_core.cuh: TwSmemPair)
+        const int k1 = i / LN, tt = i % LN;
+        twN[2 * ((k1 >> 1) * LN + tt) + (k1 & 1)] = twN_g[i];
+    }
     for (int i = threadIdx.x; i < 32; i += THREADS) {
         twM[i] = twM_g[i];
         twh_s[i] = twh_g[i];
@@ -301,7 +304,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
         {
             const int kx = job / NB / npairs;
             const float4 *Fm = (vol == 2 ? F2c : Fc) + (size_t)(kx * NB + b) * HC * N;   // + c*N + kz
-            const TwSmem<LN> tw{twN + tN};
+            const TwSmemPair<LN> tw{reinterpret_cast<const float4 *>(twN) + tN};
 #pragma unroll 1
             for (int it = 0; it < CIT; ++it) {
                 const int c = (warp + it * NW) * GN + gN;
@@ -550,12 +553,15 @@ cls_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_
         la[L * m] = 0.f; lb[L * m] = 0.f;
         ra[L * m] = 0; rb[L * m] = 0;
     }
-    for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = twN_g[i];
+    for (int i = threadIdx.x; i < N; i += THREADS) {        // twiddles in pairs (fft_core.cuh: TwSmemPair)
+        const int k1 = i / L, tt = i % L;
+        tws[2 * ((k1 >> 1) * L + tt) + (k1 & 1)] = twN_g[i];
+    }
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
     const uint32_t tcol = *tslot + ((uint32_t)(32 * warp) << 16);
-    const TwSmem<L> tw{tws + t};
+    const TwSmemPair<L> tw{reinterpret_cast<const float4 *>(tws) + t};
     // class twiddles of this thread's column of the combine pass: W_N^(n' b), W_N^((n'+1) b)
     const int cpp = W4 == 8 ? threadIdx.x / (THREADS / PPT) : threadIdx.x % PPT;
     C2 twc[NB - 1];
@@ -605,7 +611,11 @@ cls_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_
                 for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + RS * n1 + u0);
                 DftReg<E, C2>::run(v);
 #pragma unroll
-                for (int k1 = 1; k1 < E; ++k1) v[k1] = cmulw(v[k1], tw(k1));
+                for (int k = 0; k < E / 2; ++k) {
+                    const float4 w = tw.pair(k);
+                    if (k > 0) v[2 * k] = cmulw(v[2 * k], make_float2(w.x, w.y));
+                    v[2 * k + 1] = cmulw(v[2 * k + 1], make_float2(w.z, w.w));
+                }
                 __syncwarp();
 #pragma unroll
                 for (int k1 = 0; k1 < E; ++k1) sts_c2(tile + RS * k1 + (u0 ^ G::xc(k1 & (L - 1))), v[k1]);
