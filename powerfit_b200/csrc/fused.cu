@@ -594,8 +594,12 @@ fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint3
                         const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
                         const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
                         const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
-                        if (((ma >> m) & 1u) && ca > lba[8 * m].x) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
-                        if (((mb >> m) & 1u) && cb > lbb[8 * m].x) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
+                        // the running best is read unconditionally: only a third of a percent of the warps have no
+                        // lcc_mask bit in any lane, so a branch around the load only adds BSSY/BSYNC pairs
+                        const float cura = lba[8 * m].x, curb = lbb[8 * m].x;
+                        const bool ua = ((ma >> m) & 1u) != 0 && ca > cura, ub = ((mb >> m) & 1u) != 0 && cb > curb;
+                        if (ua) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
+                        if (ub) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
                     }
                 }
             }

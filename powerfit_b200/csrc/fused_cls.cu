@@ -665,8 +665,11 @@ cls_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_
                                 const bool sb = have_b && (vb.y > va.y || !(va.y == va.y));
                                 const float ca = sa ? vb.x : va.x, cb = sb ? vb.y : va.y;          // NaN never passes '>'
                                 const uint16_t ja = (uint16_t)(ia - rot0 + (sa ? 1u : 0u)), jb = (uint16_t)(ia - rot0 + (sb ? 1u : 0u));
-                                if (((ma >> m) & 1u) && ca > la[L * m]) { la[L * m] = ca; ra[L * m] = ja; }
-                                if (((mb >> m) & 1u) && cb > lb[L * m]) { lb[L * m] = cb; rb[L * m] = jb; }
+                                // unconditional read, predicated stores (see fused_ifftx_lcc_tma_kernel)
+                                const float cura = la[L * m], curb = lb[L * m];
+                                const bool ua = ((ma >> m) & 1u) != 0 && ca > cura, ub = ((mb >> m) & 1u) != 0 && cb > curb;
+                                if (ua) { la[L * m] = ca; ra[L * m] = ja; }
+                                if (ub) { lb[L * m] = cb; rb[L * m] = jb; }
                             }
                         }
                     }
