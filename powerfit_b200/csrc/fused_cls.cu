@@ -603,8 +603,11 @@ cls_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_
         const int p = p0 + item / 3, vi = item % 3;
         const uint32_t ia = (uint32_t)(first_index + 2 * p);
         const bool have_b = 2 * p + 1 < count;
-        auto run_item = [&](auto vi_tag) {
-            constexpr int VI = decltype(vi_tag)::value;
+        // ONE body for the three volume kinds (VI = 0 ave2, 1 ave, 2 gcc; warp-uniform): 1/sqrt(var) waits in TMEM,
+        // not in registers, so nothing ties a kind to its own code -- and three unrolled copies of the transform
+        // (4 096 instructions at N = 192) showed up as instruction-fetch stalls (no_instruction 0.55)
+        {
+            const int VI = vi;
             {
                 C2 v[E];
 #pragma unroll
@@ -676,10 +679,7 @@ cls_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_
                 }
             }
             if (VI != 2) tmem_wait_st();
-        };
-        if (vi == 0) run_item(std::integral_constant<int, 0>{});
-        else if (vi == 1) run_item(std::integral_constant<int, 1>{});
-        else run_item(std::integral_constant<int, 2>{});
+        }
     }
 #pragma unroll
     for (int m = 0; m < E; ++m) {
