@@ -358,7 +358,7 @@ def strong_search(dev, rank, world, batch):
             "result": {"nonzero": checksum[0], "lcc_max": checksum[1], "rot_at_max": checksum[2]}}
 
 
-def multi_template_search(dev, rank, world, rot_per_template=600):
+def multi_template_search(dev, rank, world, rot_per_template=2000):
     """BASELINE configs[4] shape: FOUR distinct sub-unit templates against one 192^3 map (plain LCC), `rot_per_template`
     rotations each, through MultiTemplateCorrelator.scan_all(): one plan (FT(map), FT(map^2), work buffers shared),
     one template slot per sub-unit, (template, rotation block) work items dealt over the ranks, ONE MAX all-reduce
