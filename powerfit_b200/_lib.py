@@ -45,20 +45,40 @@ def build(force=False, verbose=False):
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    # link into a scratch name and rename: a reader (a loader, a snapshot of the tree) never sees a partial file
-    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + srcs
+    # one nvcc per translation unit, side by side (fused.cu alone instantiates ~60 kernels), then one link; the
+    # library appears under its final name by rename, so a reader (a loader, a snapshot of the tree) never sees a
+    # partial file
+    import concurrent.futures
+    import shutil
+    import tempfile
+    objdir = tempfile.mkdtemp(prefix="pfb_build_")
+    log = []
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    try:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+            results = list(ex.map(compile_one, srcs))
+        for src, obj, res in results:
+            if res.returncode != 0:
+                raise PowerfitB200Error("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+            log.append(res.stderr)
+        tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+        res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", tmp] + [obj for _, obj, _ in results],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise PowerfitB200Error("nvcc link failed:\n" + res.stdout + res.stderr)
+        os.replace(tmp, LIB_PATH)
+    finally:
+        shutil.rmtree(objdir, ignore_errors=True)
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        if os.path.exists(tmp):
-            os.remove(tmp)
-        raise PowerfitB200Error("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(tmp, LIB_PATH)
-    if verbose:
-        print(res.stderr)
+        print("\n".join(log))
     return LIB_PATH
 
 

@@ -44,29 +44,46 @@ def shard_bounds(nrot, world, rank):
     return lo, hi
 
 
-FUSED_CUBES = (64, 128, 192, 256)
+FUSED_AXES = (32, 64, 96, 128)        # any mix of these per axis (csrc/fused.cu)
+FUSED_CUBES = (192, 256)              # cubes only (csrc/fused_cls.cu)
+
+
+def fused_shape(shape):
+    """Smallest grid with a fused pipeline that holds `shape`: every axis rounded up to 32, 64, 96 or 128 voxels,
+    a 192^3 or 256^3 cube when an axis is longer than 128, None above 256."""
+    if max(shape) <= FUSED_AXES[-1]:
+        return tuple(min(n for n in FUSED_AXES if n >= s) for s in shape)
+    for n in FUSED_CUBES:
+        if max(shape) <= n:
+            return (n, n, n)
+    return None
 
 
 def fused_cube(shape):
-    """Edge of the smallest cubic grid with a fused pipeline that holds `shape`, or None."""
-    for n in FUSED_CUBES:
+    """Edge of the smallest CUBIC grid with a fused pipeline that holds `shape`, or None."""
+    for n in (64, 128, 192, 256):
         if max(shape) <= n:
             return n
     return None
 
 
+def _as_shape(n):
+    return (n, n, n) if np.isscalar(n) else tuple(int(v) for v in n)
+
+
 def pad_target(a, n):
-    """Zero-pad a map at the high end of every axis to n^3 (what the reference CLI's `extend` does,
-    volume.py:102-118, just further)."""
-    out = np.zeros((n, n, n), dtype=a.dtype)
+    """Zero-pad a map at the high end of every axis to the shape n (an int means n^3) -- what the reference CLI's
+    `extend` does (volume.py:102-118), just further."""
+    out = np.zeros(_as_shape(n), dtype=a.dtype)
     out[:a.shape[0], :a.shape[1], :a.shape[2]] = a
     return out
 
 
 def pad_wrapped(a, n):
     """Zero-pad a template / mask that is centred on voxel 0 with wrap-around: non-negative offsets stay at
-    the low end of every axis, negative offsets move to the high end of the n^3 grid."""
-    out = np.zeros((n, n, n), dtype=a.dtype)
+    the low end of every axis, negative offsets move to the high end of the grid of shape n (an int means n^3)."""
+    shape = _as_shape(n)
+    out = np.zeros(shape, dtype=a.dtype)
     cuts = [s // 2 + 1 for s in a.shape]
     for sz in (0, 1):
         for sy in (0, 1):
@@ -77,7 +94,7 @@ def pad_wrapped(a, n):
                     if side == 0:
                         src.append(slice(0, h)); dst.append(slice(0, h))
                     else:
-                        src.append(slice(h, length)); dst.append(slice(n - (length - h), n))
+                        src.append(slice(h, length)); dst.append(slice(shape[ax] - (length - h), shape[ax]))
                 out[tuple(dst)] = a[tuple(src)]
     return out
 
@@ -108,8 +125,9 @@ class CUDACorrelator(object):
         """``shard=True`` (opt-in): split the rotation list over the ranks of the torch.distributed process
         group ``group`` (default: the world group) and merge with one MAX all-reduce, see ``scan``.
 
-        ``pad=True`` (opt-in, not reference behaviour): zero-pad the map to the next cubic grid that has
-        a fused pipeline (64, 128, 192 or 256 voxels) and crop the results back.  The result is exactly
+        ``pad=True`` (opt-in, not reference behaviour): zero-pad the map to the next grid that has a fused
+        pipeline (every axis up to 32, 64, 96 or 128 voxels; 192^3 / 256^3 beyond) and crop the results back.
+        Grids whose axes already are such lengths take the fused pipeline without it.  The result is exactly
         the search on the padded map -- what the reference computes when its own `extend` step
         (powerfit.py:230-233) is given that size -- and about ten times faster than the any-shape pipeline;
         near the box faces it differs from the unpadded search, whose template wraps around."""
@@ -121,8 +139,8 @@ class CUDACorrelator(object):
             raise ValueError("target must be a 3-D array")
         self._crop = None
         if pad:
-            n = fused_cube(target.shape)
-            if n is not None and target.shape != (n, n, n):
+            n = fused_shape(target.shape)
+            if n is not None and target.shape != n:
                 self._crop = target.shape
                 target = pad_target(target, n)
         if prep not in ("device", "host"):
@@ -229,7 +247,7 @@ class CUDACorrelator(object):
     def template(self, template):                      # powerfitter.py:236-243
         template = np.asarray(template)
         if self._crop is not None and template.shape == self._crop:
-            template = pad_wrapped(template, self._shape[0])
+            template = pad_wrapped(template, self._shape)
         if template.shape != self._shape:
             raise ValueError("Shape of template does not match the target.")
         self._mask = None
@@ -246,7 +264,7 @@ class CUDACorrelator(object):
             raise ValueError("First set the template.")
         mask = np.asarray(mask)
         if self._crop is not None and mask.shape == self._crop:
-            mask = pad_wrapped(mask, self._shape[0])
+            mask = pad_wrapped(mask, self._shape)
         if self._shape != mask.shape:
             raise ValueError("Shape of the mask is different from target.")
         torch = self._torch

@@ -215,7 +215,7 @@ int pfb_plan_destroy(pfb_plan *h) {
         if (p->slots[i].tmplq) cudaFree(p->slots[i].tmplq);
     }
     void *ptrs[] = {p->tw[0], p->tw[1], p->tw[2], p->tmpl, p->mask, p->lcc_mask, p->F, p->F2,
-                    p->A, p->B, p->rot_dev, p->best_scratch, p->prep_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->mbits, p->tmplq,
+                    p->A, p->B, p->rot_dev, p->best_scratch, p->prep_scratch, p->Fq, p->F2q, p->twdN, p->twdM, p->twdX, p->mbits, p->tmplq,
                     p->cls_twN, p->cls_twM, p->cls_twh, p->cls_fold};
     for (void *q : ptrs)
         if (q) cudaFree(q);

@@ -129,10 +129,11 @@ struct Plan {
     float *tmpl = nullptr, *mask = nullptr;        // prepared template, mask (float32)
     uint8_t *lcc_mask = nullptr;
     float2 *F = nullptr, *F2 = nullptr;            // conj(P f)/V, conj(P f^2)/V, full spectra
-    // fused path (cubic 64/128): map spectra transposed to [kx][ky][kz], template support box
+    // fused path (axes of 64/128, cubic 192/256): map spectra transposed to [kx][ky][kz], template support box
     bool fused = false;
     float2 *Fq = nullptr, *F2q = nullptr;
-    float2 *twdN = nullptr, *twdM = nullptr;       // packed-pencil twiddle tables [k1][t] (fft_core.cuh)
+    float2 *twdN = nullptr, *twdM = nullptr;       // packed-pencil twiddle tables [k1][t] (fft_core.cuh): z columns, y rows
+    float2 *twdX = nullptr;                        // the same for kernel C's x pencils (8 lanes x nx/8)
     float4 *tmplq = nullptr;                       // template corner table for kernel A's gather
     uint32_t *mbits = nullptr;                     // lcc_mask bit-packed in kernel C's lane layout
     CUtensorMap tmapC;                             // kernel C's view of the X2 work buffer (tma.cuh)

@@ -247,9 +247,34 @@ template <class T> __device__ __forceinline__ void dft24(T (&v)[24]) {
     }
 }
 
+// 12-point DFT, natural order in and out: n = n0 + 3 n1, k = k1 + 4 k0
+template <class T> __device__ __forceinline__ void dft12(T (&v)[12]) {
+    T t[3][4];
+#pragma unroll
+    for (int n0 = 0; n0 < 3; ++n0) {
+#pragma unroll
+        for (int n1 = 0; n1 < 4; ++n1) t[n0][n1] = v[n0 + 3 * n1];
+        dft4(t[n0][0], t[n0][1], t[n0][2], t[n0][3]);
+    }
+    // t[n0][k1] *= W12^(n0 k1)
+    t[1][1] = rotc(t[1][1], 0.86602540378443865f, 0.5f);                    // W12^1
+    t[1][2] = rotc(t[1][2], 0.5f, 0.86602540378443865f);                    // W12^2
+    t[1][3] = mul_i(t[1][3]);                                               // W12^3
+    t[2][1] = rotc(t[2][1], 0.5f, 0.86602540378443865f);                    // W12^2
+    t[2][2] = rotc(t[2][2], -0.5f, 0.86602540378443865f);                   // W12^4
+    t[2][3] = cneg(t[2][3]);                                                // W12^6
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        dft3(t[0][k1], t[1][k1], t[2][k1]);
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) v[k1 + 4 * k0] = t[k0][k1];
+    }
+}
+
 template <int E, class T> struct DftReg;
 template <class T> struct DftReg<4, T> { static __device__ __forceinline__ void run(T (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); } };
 template <class T> struct DftReg<8, T> { static __device__ __forceinline__ void run(T (&v)[8]) { dft8(v); } };
+template <class T> struct DftReg<12, T> { static __device__ __forceinline__ void run(T (&v)[12]) { dft12(v); } };
 template <class T> struct DftReg<16, T> { static __device__ __forceinline__ void run(T (&v)[16]) { dft16(v); } };
 template <class T> struct DftReg<24, T> { static __device__ __forceinline__ void run(T (&v)[24]) { dft24(v); } };
 

@@ -1,4 +1,5 @@
-// Fused three-kernel search pipeline for cubic grids of N = 64 or 128 voxels.
+// Fused three-kernel search pipeline for grids whose axes are 32, 64, 96 or 128 voxels long (any mix: the x
+// pencils of kernels A and C are templated on nx, kernel B's plane on (nz, ny); 64^3 and 128^3 are the tuned cases).
 //
 //   A  fused_rotate_fftx  : rotate template+mask (a PAIR of rotations packed as one complex
 //                           signal: re = rotation a, im = rotation b), transform along x,
@@ -38,13 +39,15 @@ namespace pfb {
 
 // ------------------------------------------------------------------------------- kernel A
 // L lanes per x pencil (E = N / L points each); 32 rows per CTA -> 32 L threads
+// N = nx (the pencil length); ny and nz are run-time
 template <int N, int L>
 __global__ void __launch_bounds__(32 * L)
 fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict__ mask,
                          const double *__restrict__ rot, int first, int count, int nsig,
                          float2 *__restrict__ X1, const float2 *__restrict__ twN, int rs, int rs2,
-                         unsigned ymask, int nzv) {
+                         unsigned ymask, int nzv, int ny, int nz) {
     constexpr int E = N / L, TP = 33, THREADS = 32 * L;
+    const int rmax = min(N, min(ny, nz)) / 2;
     extern __shared__ float2 smem[];
     float2 *tile_t = smem, *tile_m = smem + N * TP;
     const int pair = blockIdx.y;
@@ -54,12 +57,12 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
         if (mbits & 1u) { if (yt_rank == 0) break; --yt_rank; }
         mbits >>= 1;
     }
-    const int z = (j - rs + N) % N, y0 = 32 * ytile;
-    const GridDims d{N, N, N, N / 2, (long)N * N * N};
+    const int z = (j - rs + nz) % nz, y0 = 32 * ytile;
+    const GridDims d{nz, ny, N, rmax, (long)nz * ny * N};
     const int ra = first + 2 * pair;
     const bool have_b = 2 * pair + 1 < count;
     const double *Ra = rot + (long)ra * 9, *Rb = Ra + 9;
-    const int oz = z <= N / 2 ? z : z - N;
+    const int oz = z <= nz / 2 ? z : z - nz;
 
     // ---- gather the 32 x N tile of both signals (zeros outside the sphere / support)
     //      zero-fill first, then visit only the x offsets inside the support box [xlo, rs];
@@ -70,14 +73,14 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
     }
     __syncthreads();
     const int xlo = max(-rs, -(N / 2 - 1)), W = rs - xlo + 1;
-    const int lim2 = min(rs2, (N / 2) * (N / 2));
+    const int lim2 = min(rs2, rmax * rmax);
     // both rotations of a position are fetched before either is blended (six gathers in flight); an odd
     // last pair samples rotation a twice and discards the copy
     const double *Rb2 = have_b ? Rb : Ra;
     for (int idx = threadIdx.x; idx < 32 * W; idx += THREADS) {
         const int r = idx / W, ox = idx % W + xlo;
         const int iy = y0 + r;
-        const int oy = iy <= N / 2 ? iy : iy - N;
+        const int oy = iy <= ny / 2 ? iy : iy - ny;
         if (ox * ox + oy * oy + oz * oz <= lim2) {
             const SrcCoord ca = source_coord(Ra, ox, oy, oz), cb = source_coord(Rb2, ox, oy, oz);
             const float ta = sample_trilinear_q(tmplq, d, ca), tb = sample_trilinear_q(tmplq, d, cb);
@@ -112,11 +115,11 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
 
     // ---- coalesced write-out: 32 consecutive y (256 B) per kx, pairs of y interleaved
     //      (re[y], re[y+1], im[y], im[y+1]) -- the layout kernel B's packed passes work in
-    constexpr int H = N / 2;
+    const int H = ny / 2;
     const size_t slab = (size_t)N * H;
     float4 *X14 = reinterpret_cast<float4 *>(X1);
-    float4 *o_t = X14 + ((size_t)(pair * nsig + 0) * N + z) * slab + y0 / 2;      // X1[pair][sig][z][kx][y/2]
-    float4 *o_m = X14 + ((size_t)(pair * nsig + 1) * N + z) * slab + y0 / 2;
+    float4 *o_t = X14 + ((size_t)(pair * nsig + 0) * nz + z) * slab + y0 / 2;      // X1[pair][sig][z][kx][y/2]
+    float4 *o_m = X14 + ((size_t)(pair * nsig + 1) * nz + z) * slab + y0 / 2;
     for (int idx = threadIdx.x; idx < 16 * N; idx += THREADS) {
         const int kx = idx >> 4, jj = idx & 15;
         const float2 a = tile_t[kx * TP + 2 * jj], b = tile_t[kx * TP + 2 * jj + 1];
@@ -130,7 +133,7 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
 #pragma unroll
         for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + r] = v2[m];
         __syncthreads();
-        float4 *o_2 = X14 + ((size_t)(pair * nsig + 2) * N + z) * slab + y0 / 2;
+        float4 *o_2 = X14 + ((size_t)(pair * nsig + 2) * nz + z) * slab + y0 / 2;
         for (int idx = threadIdx.x; idx < 16 * N; idx += THREADS) {
             const int kx = idx >> 4, jj = idx & 15;
             const float2 a = tile_t[kx * TP + 2 * jj], b = tile_t[kx * TP + 2 * jj + 1];
@@ -147,10 +150,28 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
 //   phase 2  columns ky and ky+N/2 as two independent pencils: forward z, multiply with the
 //            map spectrum (stored in the same pairing, Fpk[kx][ky][kz]), inverse z
 //   phase 3  rows, inverse y : split-in -> adjacent-out, straight to X2
-template <int N> struct FusedCfg;
-// CTAS: persistent CTAs of kernel B per SM (a 64^3 plane is 34 KB, so two fit and overlap their phases)
-template <> struct FusedCfg<64> { static constexpr int LN = 8, EN = 8, LM = 4, EM = 8, CTAS = 2; };
-template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8, EM = 8, CTAS = 1; };
+// Pencil geometry per axis length: column (z) pencils of L x E points, row (y) pencils of LM x EM packed pairs.
+template <int N> struct AxisCfg;
+template <> struct AxisCfg<32> { static constexpr int L = 4, E = 8, LM = 4, EM = 4; };
+template <> struct AxisCfg<64> { static constexpr int L = 8, E = 8, LM = 4, EM = 8; };
+template <> struct AxisCfg<96> { static constexpr int L = 4, E = 24, LM = 4, EM = 12; };      // 24 = 3 x 8, 12 = 3 x 4
+template <> struct AxisCfg<128> { static constexpr int L = 8, E = 16, LM = 8, EM = 8; };
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr uint32_t pow2ceil(uint32_t v) { uint32_t r = 32; while (r < v) r *= 2; return r; }
+// Kernel B of an (NZ, NY) plane: one warp per group of 32 / LN column pairs -> NY LN / 2 threads (512 at 128 x 128,
+// where one CTA fills the register file; 256 at 64 x 64, where two CTAs per SM overlap their phases); as many CTAs
+// per SM as registers (128 per thread, 232 with 24-point register DFTs) and shared memory allow, at most four
+template <int NZ, int NY> struct FusedCfg {
+    static constexpr int LN = AxisCfg<NZ>::L, EN = AxisCfg<NZ>::E, LM = AxisCfg<NY>::LM, EM = AxisCfg<NY>::EM;
+    static constexpr int THREADS = NY * LN / 2, REGS = EN >= 24 ? 232 : 128;
+    static constexpr size_t PLANE = (size_t)(NZ * (NY / 2 + 1)) * sizeof(float4) + (size_t)(NZ + NY) * sizeof(float2) + 128;
+    static constexpr int CTAS = cmax(1, cmin(4, cmin((int)(227 * 1024 / (PLANE + 1024)), 65536 / (THREADS * REGS))));
+    // the TMEM stash of a binary mask's spectrum (tmem.cuh moves 8 packed pairs at a time: 8-lane column pencils);
+    // without it the mask is transformed forward twice, once per product
+    static constexpr bool STASH = LN == 8;
+    static constexpr uint32_t TCOLS = pow2ceil((uint32_t)((THREADS / 32 + 3) / 4 * 4 * EN));
+};
 
 // Persistent: one CTA per SM walks jobs j = blockIdx.x, + gridDim.x, ...; a job is one (pair, kx) and consists
 // of the three output planes gcc, ave, ave2 in that order.  The row loop does phase 3 of the current plane and
@@ -171,20 +192,25 @@ template <> struct FusedCfg<128> { static constexpr int LN = 8, EN = 16, LM = 8,
 // profiles/r02_ncu_v1_fused_full.txt) but are copied by TMA -- two 3-D boxes, rows z = 0..rs and z = N-rs..N-1 of
 // the (pair, signal, kx) plane of X1, issued by one thread while phase 2 runs -- into a staging area behind the
 // plane, and the row loop reads them from shared memory.  Used when the staging area fits (2 rs + 2 rows).
-template <int N, int THREADS, bool STAGED>
-__global__ void __launch_bounds__(THREADS, FusedCfg<N>::CTAS)
+// NZ x NY: the plane (z rows, y columns); the number of planes per volume is the constant NXT, or run-time (nx_rt)
+// when NXT = 0 (the cubes keep it a constant: one more live register spills in the 128^3 kernel).
+template <int NZ, int NY, int NXT, bool STAGED>
+__global__ void __launch_bounds__(FusedCfg<NZ, NY>::THREADS, FusedCfg<NZ, NY>::CTAS)
 fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fpk,
                        const float4 *__restrict__ F2pk, const float2 *__restrict__ twN_g,
                        const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g, int rs,
-                       unsigned ymask, int nsig, int npairs, const __grid_constant__ CUtensorMap tmapX1) {
-    using Cfg = FusedCfg<N>;
-    constexpr int H = N / 2, P = H + 1;
+                       unsigned ymask, int nsig, int npairs, int nx_rt, const __grid_constant__ CUtensorMap tmapX1) {
+    using Cfg = FusedCfg<NZ, NY>;
+    const int nx = NXT ? NXT : nx_rt;
+    constexpr int N = NZ, THREADS = Cfg::THREADS;              // N: rows of the plane = length of the column pencils
+    constexpr int H = NY / 2, P = H + 1;
     constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
     constexpr int LM = Cfg::LM, EM = Cfg::EM, GM = 32 / LM;      // row pencils: packed N/2 points
     constexpr int NW = THREADS / 32;
-    constexpr uint32_t TCOLS = NW * EN;                          // TMEM columns: 4 EN per warp, 4 warps per lane quarter
+    constexpr bool STASH = Cfg::STASH;
+    constexpr uint32_t TCOLS = Cfg::TCOLS;                       // TMEM columns: 4 EN per warp, 4 warps per lane quarter
     static_assert(H / GN == NW, "one column group per warp: the TMEM stash is indexed by warp");
-    static_assert(TCOLS >= 32 && (TCOLS & (TCOLS - 1)) == 0 && TCOLS * Cfg::CTAS <= 512, "TMEM allocation");
+    static_assert(!STASH || TCOLS * Cfg::CTAS <= 512, "TMEM allocation");
     extern __shared__ float4 smem4[];
     float4 *plane = smem4;                                        // [N][P]
     float2 *twN = reinterpret_cast<float2 *>(plane + N * P);      // [EN][LN] W_N^(t k1)
@@ -194,16 +220,17 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     uint64_t *sbar = reinterpret_cast<uint64_t *>(tslot + 2);                          // staging copies have landed
     // staging rows: zi = z for z <= rs, zi = rs + 1 + (z - (N - rs)) for the rows below zero; 128-byte aligned
     float4 *stage = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(sbar + 1) + 112);
-    const size_t slab = (size_t)N * H;                                                 // float4 per z
+    const size_t slab = (size_t)nx * H;                                                // float4 per z
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // LM = 4: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo the
     // 128-byte bank window (P odd), instead of two neighbouring rows that would collide
     const int tM = lane & (LM - 1), gM = LM == 4 ? (lane >> 3) + 4 * ((lane >> 2) & 1) : lane / LM;
     const int tN = lane & (LN - 1), gN = lane / LN;
     const int nzv = min(2 * rs + 1, N);
-    const bool binary = nsig == 2;
+    const bool binary = STASH && nsig == 2;
+    auto sig_of = [&](int v) { return v < nsig ? v : nsig - 1; };      // ave2 of a binary mask without stash: the mask again
     // job -> (pair, kx), pair fastest: the jobs in flight at any time share their map-spectrum planes (kx)
-    const int njobs = npairs * N;
+    const int njobs = npairs * nx;
 
     int job = blockIdx.x, vol = 0;      // plane whose phase 1 comes next
     int cjob = -1, cvol = 0;            // plane whose phase 2 is done (phase 3 pending)
@@ -213,13 +240,13 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
         twN[2 * ((k1 >> 1) * LN + tt) + (k1 & 1)] = twN_g[i];
     }
     for (int i = threadIdx.x; i < H; i += THREADS) { twM[i] = twM_g[i]; twh_s[i] = twh_g[i]; }
-    if (warp == 0) tmem_alloc(tslot, TCOLS);
+    if (STASH && warp == 0) tmem_alloc(tslot, TCOLS);
     // one thread: both boxes of plane (j, v) of X1 -> staging area
     auto stage_issue = [&](int j, int v) {
         const int pair = j % npairs, kx = j / npairs;
         mbar_arrive_expect_tx(sbar, (uint32_t)(2 * (rs + 1) * H * sizeof(float4)));
-        tma_load_4d(stage, &tmapX1, sbar, 0, kx, 0, pair * nsig + v);
-        tma_load_4d(stage + (rs + 1) * H, &tmapX1, sbar, 0, kx, N - rs, pair * nsig + v);   // last row out of bounds: zeros
+        tma_load_4d(stage, &tmapX1, sbar, 0, kx, 0, pair * nsig + sig_of(v));
+        tma_load_4d(stage + (rs + 1) * H, &tmapX1, sbar, 0, kx, N - rs, pair * nsig + sig_of(v));   // last row out of bounds: zeros
     };
     if (STAGED && threadIdx.x == 0) {
         mbar_init(sbar, 1);
@@ -231,7 +258,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
     __syncthreads();
     tmem_fence_after_sync();
     // this warp's stash: lane quarter warp % 4 (the only one a warp may address), 4 EN columns
-    const uint32_t tcol = *tslot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * EN);
+    const uint32_t tcol = STASH ? *tslot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * EN) : 0u;
 
     while (true) {
         __syncthreads();          // phase 2 of the current plane is complete (first pass: the tables are in place)
@@ -247,7 +274,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
             const float4 *src = X1;
             if (fwd) {
                 const int pair = job % npairs, kx = job / npairs;
-                src = X1 + (size_t)(pair * nsig + vol) * N * slab + (size_t)kx * H;    // + z*slab + y/2
+                src = X1 + (size_t)(pair * nsig + sig_of(vol)) * N * slab + (size_t)kx * H;    // + z*slab + y/2
             }
             float4 *dst = X2;
             if (cjob >= 0) {
@@ -310,7 +337,7 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
                     const int pair = jn % npairs, kx = jn / npairs;
                     const int j = threadIdx.x / (2 * __popc(ymask)), l = threadIdx.x % (2 * __popc(ymask));
                     const int z = (j - rs + N) % N, tile = __fns(ymask, 0, (l >> 1) + 1);
-                    const float4 *a = X1 + (size_t)(pair * nsig + vn) * N * slab + (size_t)kx * H + (size_t)z * slab +
+                    const float4 *a = X1 + (size_t)(pair * nsig + sig_of(vn)) * N * slab + (size_t)kx * H + (size_t)z * slab +
                                       16 * tile + 8 * (l & 1);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
                 }
@@ -331,20 +358,24 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
                     const int sz = z <= N / 2 ? z : z - N;
                     v[n1] = (sz >= -rs && sz <= rs) ? lds_c2(plane + z * P + ky) : c2_zero();
                 }
-                fft_pencil2_mul_stash<false, LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN, tcol,
-                                                     binary && vol == 1);
+                if constexpr (STASH)
+                    fft_pencil2_mul_stash<false, LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN, tcol,
+                                                         binary && vol == 1);
+                else
+                    fft_pencil2_mul<LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN);
             } else {
-                fft_pencil2_mul_stash<true, LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN, tcol, false);
+                if constexpr (STASH)
+                    fft_pencil2_mul_stash<true, LN, EN>(v, plane + ky, P, tN, tw, Fm + (size_t)ky * N + tN, tcol, false);
             }
             fft_pencil2<LN, EN>(v, plane + ky, P, tN, tw);
 #pragma unroll
             for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + ky, v[m]);
-            tmem_wait_st();       // the parked spectrum is in place before this thread passes the next barrier
+            if (STASH) tmem_wait_st();       // the parked spectrum is in place before this thread passes the next barrier
         }
         cjob = job; cvol = vol;
         if (++vol == 3) { vol = 0; job += gridDim.x; }
     }
-    if (warp == 0) tmem_dealloc(*tslot, TCOLS);
+    if (STASH && warp == 0) tmem_dealloc(*tslot, TCOLS);
 }
 
 // ------------------------------------------------------------------------------- kernel C
@@ -359,39 +390,41 @@ fused_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, c
 // RT rows per tile (16 by default, 32 with PFB_C_RT=32): 8 lanes per y pair -> 4 RT threads; 96 / RT CTAs per SM.
 // Measured at 128^3: 5.28 us/rotation with 16-row tiles (six 64-thread CTAs per SM interleave their load and
 // compute phases more finely), 5.61 with 32 rows, 5.85 with 8.
-template <int N, int RT>
-__global__ void __launch_bounds__(4 * RT, 96 / RT)
+// L lanes per x pencil (8 for the 64- and 128-point pencils, 4 for 32 = 4 x 8 and 96 = 4 x 24).
+template <int N, int L, int RT>
+__global__ void __launch_bounds__(L * RT / 2, L == 8 ? 96 / RT : (N / L >= 24 ? 4 : 8))
 fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict__ mbits, float norm,
                        int first_index, int count, int pairs_per_chunk, int64_t *__restrict__ best,
-                       const float2 *__restrict__ twN_g) {
-    constexpr int E = N / 8, H = N / 2, NP = RT / 2, TP = NP + 1, BP = N + 4, THREADS = 4 * RT, NBUF = 1;
+                       const float2 *__restrict__ twN_g, int ny, int nz) {
+    constexpr int E = N / L, NP = RT / 2, TP = NP + 1, BP = N + 4, THREADS = L * RT / 2, NBUF = 1;
+    const int H = ny / 2;
     extern __shared__ float4 smem4[];
     float4 *tile0 = smem4;                                            // [NBUF][N][TP]
     // running best of the chunk as (LCC, rotation) pairs: rotations arrive in increasing order, so a
     // strict float '>' against a +0.0 start is exactly the packed-key order (common.cuh)
     float2 *lbest = reinterpret_cast<float2 *>(tile0 + NBUF * N * TP);     // [RT][BP] (lcc, rot index bits)
-    float2 *tws = reinterpret_cast<float2 *>(lbest + RT * BP);        // [E][8] W_N^(t k1)
+    float2 *tws = reinterpret_cast<float2 *>(lbest + RT * BP);        // [E][L] W_N^(t k1)
     const int y0 = RT * blockIdx.x, z = blockIdx.y;
     const int npairs = (count + 1) / 2;
     const int p0 = blockIdx.z * pairs_per_chunk, p1 = min(npairs, p0 + pairs_per_chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = lane & 7, rp = 4 * warp + (lane >> 3);              // y pair: rows y0+2rp, y0+2rp+1
+    const int t = lane & (L - 1), rp = (32 / L) * warp + lane / L;     // y pair: rows y0+2rp, y0+2rp+1
     const size_t slab = (size_t)N * H;
-    const size_t rowa = ((size_t)z * N + y0 + 2 * rp) * N, rowb = rowa + N;
+    const size_t rowa = ((size_t)z * ny + y0 + 2 * rp) * N, rowb = rowa + N;
     float2 *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
-    // bit m of a row's word t: lcc_mask at x = t + 8 m (built once per target by mask_bits_kernel)
-    const unsigned ma = mbits[((size_t)z * N + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * N + y0 + 2 * rp + 1) * 8 + t];
+    // bit m of a row's word t: lcc_mask at x = t + L m (built once per target by mask_bits_kernel)
+    const unsigned ma = mbits[((size_t)z * ny + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * ny + y0 + 2 * rp + 1) * 8 + t];
 #pragma unroll
     for (int m = 0; m < E; ++m) {
-        lba[8 * m] = make_float2(0.f, 0.f);
-        lbb[8 * m] = make_float2(0.f, 0.f);
+        lba[L * m] = make_float2(0.f, 0.f);
+        lbb[L * m] = make_float2(0.f, 0.f);
     }
     for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = twN_g[i];
-    const TwSmem<8> tw{tws + t};
+    const TwSmem<L> tw{tws + t};
     const int nitems = 3 * (p1 - p0);
     auto prefetch = [&](int item) {
         const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
-        const float4 *src = X2 + ((size_t)(p * 3 + vol) * N + z) * slab + y0 / 2;
+        const float4 *src = X2 + ((size_t)(p * 3 + vol) * nz + z) * slab + y0 / 2;
         float4 *tile = tile0 + (item % NBUF) * N * TP;
         for (int idx = threadIdx.x; idx < NP * N; idx += THREADS) {
             const int kx = idx / NP, c = idx % NP;
@@ -401,7 +434,7 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
     };
     if (nitems > 0) prefetch(0);
     C2 sd[E];
-    constexpr int Q = E / 8;
+    constexpr int Q = E / L;
     for (int item = 0; item < nitems; ++item) {
         if (NBUF == 2) {
             // the other buffer was released by the barrier at the end of the previous item
@@ -420,20 +453,20 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
             {
                 C2 v[E];
 #pragma unroll
-                for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + (t + 8 * n1) * TP + rp);
-                pencil2_stage1<8, E>(v, tile + rp, TP, t, tw);
+                for (int n1 = 0; n1 < E; ++n1) v[n1] = lds_c2(tile + (t + L * n1) * TP + rp);
+                pencil2_stage1<L, E>(v, tile + rp, TP, t, tw);
             }
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                // outputs x = t + 8 m, m = q + Q k0, of this chunk go straight into the epilogue
-                C2 a[8];
-                pencil2_stage2<8>(a, tile + rp, TP, t, q);
+                // outputs x = t + L m, m = q + Q k0, of this chunk go straight into the epilogue
+                C2 a[L];
+                pencil2_stage2<L>(a, tile + rp, TP, t, q);
                 if (q == Q - 1 && NBUF == 1) {
                     __syncthreads();       // every pencil is out of the tile: refill it while the arithmetic runs
                     if (item + 1 < nitems) prefetch(item + 1);
                 }
 #pragma unroll
-                for (int k0 = 0; k0 < 8; ++k0) {
+                for (int k0 = 0; k0 < L; ++k0) {
                     const int m = q + Q * k0;
                     if (VI == 0) {
                         sd[m] = a[k0];                                     // ave2
@@ -451,8 +484,8 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
                         const bool sb = have_b && (lb.y > la.y || !(la.y == la.y));
                         const float ca = sa ? lb.x : la.x, cb = sb ? lb.y : la.y;          // NaN never passes '>'
                         const uint32_t ja = sa ? ia + 1 : ia, jb = sb ? ia + 1 : ia;
-                        if (((ma >> m) & 1u) && ca > lba[8 * m].x) lba[8 * m] = make_float2(ca, __uint_as_float(ja));
-                        if (((mb >> m) & 1u) && cb > lbb[8 * m].x) lbb[8 * m] = make_float2(cb, __uint_as_float(jb));
+                        if (((ma >> m) & 1u) && ca > lba[L * m].x) lba[L * m] = make_float2(ca, __uint_as_float(ja));
+                        if (((mb >> m) & 1u) && cb > lbb[L * m].x) lbb[L * m] = make_float2(cb, __uint_as_float(jb));
                     }
                 }
             }
@@ -465,15 +498,15 @@ fused_ifftx_lcc_kernel(const float4 *__restrict__ X2, const uint32_t *__restrict
 #pragma unroll
     for (int m = 0; m < E; ++m) {
         if ((ma >> m) & 1u) {
-            const float2 b = lba[8 * m];
+            const float2 b = lba[L * m];
             if (b.x > 0.f)
-                atomicMax(reinterpret_cast<long long *>(best + rowa + t + 8 * m),
+                atomicMax(reinterpret_cast<long long *>(best + rowa + t + L * m),
                           (long long)pack_best(__float_as_uint(b.x), __float_as_uint(b.y)));
         }
         if ((mb >> m) & 1u) {
-            const float2 b = lbb[8 * m];
+            const float2 b = lbb[L * m];
             if (b.x > 0.f)
-                atomicMax(reinterpret_cast<long long *>(best + rowb + t + 8 * m),
+                atomicMax(reinterpret_cast<long long *>(best + rowb + t + L * m),
                           (long long)pack_best(__float_as_uint(b.x), __float_as_uint(b.y)));
         }
     }
@@ -494,7 +527,7 @@ template <int N, int NBUF>
 __global__ void __launch_bounds__(64, NBUF == 1 ? 6 : (NBUF == 2 ? 4 : 3))
 fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ mbits, float norm,
                            int first_index, int count, int pairs_per_chunk, int64_t *__restrict__ best,
-                           const float2 *__restrict__ twN_g) {
+                           const float2 *__restrict__ twN_g, int ny) {
     constexpr int RT = 16, E = N / 8, BP = N + 4, THREADS = 64, TILE = N * 8;    // TILE: float4 per tile
     extern __shared__ uint8_t smem_raw[];
     // the swizzle is a function of the shared-memory address: tiles start on a 1024-byte boundary
@@ -508,9 +541,9 @@ fused_ifftx_lcc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint3
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & 7, rp = 4 * warp + (lane >> 3);              // y pair: rows y0+2rp, y0+2rp+1
     const int u = 8 * t + (rp ^ t);
-    const size_t rowa = ((size_t)z * N + y0 + 2 * rp) * N, rowb = rowa + N;
+    const size_t rowa = ((size_t)z * ny + y0 + 2 * rp) * N, rowb = rowa + N;
     float2 *lba = lbest + (2 * rp) * BP + t, *lbb = lba + BP;
-    const unsigned ma = mbits[((size_t)z * N + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * N + y0 + 2 * rp + 1) * 8 + t];
+    const unsigned ma = mbits[((size_t)z * ny + y0 + 2 * rp) * 8 + t], mb = mbits[((size_t)z * ny + y0 + 2 * rp + 1) * 8 + t];
     const int nitems = 3 * (p1 - p0);
     auto issue = [&](int item) {                                      // thread 0 only
         const int p = p0 + item / 3, vol = 2 - item % 3;              // ave2, ave, gcc
@@ -668,31 +701,33 @@ int make_x1_tensor_map(CUtensorMap *out, const void *base, int row_floats, int n
 }
 
 // ------------------------------------------------------------------------------- helpers
-// Fpk[kx][ky][kz] = (re F[kz][ky][kx], re F[kz][ky+N/2][kx], im ..., im ...), ky < N/2: the map
+// Fpk[kx][ky][kz] = (re F[kz][ky][kx], re F[kz][ky+ny/2][kx], im ..., im ...), ky < ny/2: the map
 // spectrum in the column pairing of kernel B's phase 2
-__global__ void pair_transpose_kernel(const float2 *__restrict__ F, float4 *__restrict__ Fpk, int N) {
+__global__ void pair_transpose_kernel(const float2 *__restrict__ F, float4 *__restrict__ Fpk, int nz, int ny, int nx) {
     __shared__ float4 tl[32][33];
-    const int ky = blockIdx.z, H = N / 2;
+    const int ky = blockIdx.z, H = ny / 2;
     const int kx0 = blockIdx.x * 32, kz0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const float2 a = F[((size_t)(kz0 + i) * N + ky) * N + kx0 + threadIdx.x];
-        const float2 b = F[((size_t)(kz0 + i) * N + ky + H) * N + kx0 + threadIdx.x];
+        const float2 a = F[((size_t)(kz0 + i) * ny + ky) * nx + kx0 + threadIdx.x];
+        const float2 b = F[((size_t)(kz0 + i) * ny + ky + H) * nx + kx0 + threadIdx.x];
         tl[i][threadIdx.x] = make_float4(a.x, b.x, a.y, b.y);
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y)
-        Fpk[((size_t)(kx0 + i) * H + ky) * N + kz0 + threadIdx.x] = tl[threadIdx.x][i];
+        Fpk[((size_t)(kx0 + i) * H + ky) * nz + kz0 + threadIdx.x] = tl[threadIdx.x][i];
 }
 
-// mbits[row * 8 + t], row = z*N + y: bit m = (lcc_mask[row][t + 8 m] != 0) -- kernel C's lane layout
-__global__ void mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint32_t *__restrict__ mbits, int N, long rows) {
+// mbits[row * 8 + t], row = z*ny + y, N = nx, L lanes per x pencil: bit m of word t < L = (lcc_mask[row][t + L m] != 0)
+// -- kernel C's lane layout
+__global__ void mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint32_t *__restrict__ mbits, int N, int L, long rows) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * 8) return;
     const long row = i >> 3;
     const int t = (int)(i & 7);
     uint32_t w = 0;
-    for (int m = 0; m < N / 8; ++m)
-        if (lcc_mask[row * N + t + 8 * m]) w |= 1u << m;
+    if (t < L)
+        for (int m = 0; m < N / L; ++m)
+            if (lcc_mask[row * N + t + L * m]) w |= 1u << m;
     mbits[i] = w;
 }
 
@@ -725,14 +760,13 @@ __global__ void support_kernel(const float *__restrict__ tmpl, const float *__re
 
 // ------------------------------------------------------------------------------- host side
 // plane + twiddle tables + the TMEM base address slot + the staging barrier (padded to a 128-byte boundary) +
-// `srows` staging rows of N/2 float4 (0 = unstaged kernel)
-template <int N> static constexpr size_t smem_b(int srows) {
-    return (size_t)(N * (N / 2 + 1)) * sizeof(float4) + (size_t)(2 * N) * sizeof(float2) + 128 +
-           (size_t)srows * (N / 2) * sizeof(float4);
+// `srows` staging rows of NY/2 float4 (0 = unstaged kernel)
+template <int NZ, int NY> static constexpr size_t smem_b(int srows) {
+    return FusedCfg<NZ, NY>::PLANE + (size_t)srows * (NY / 2) * sizeof(float4);
 }
 // staging rows that fit next to the plane(s) of an SM
-template <int N> static constexpr int stage_capacity() {
-    return (int)((227 * 1024 / FusedCfg<N>::CTAS - 1024 - smem_b<N>(0)) / ((N / 2) * sizeof(float4)));
+template <int NZ, int NY> static constexpr int stage_capacity() {
+    return (int)((227 * 1024 / FusedCfg<NZ, NY>::CTAS - 1024 - smem_b<NZ, NY>(0)) / ((NY / 2) * sizeof(float4)));
 }
 template <int N> static constexpr size_t smem_c(int rt) {
     return (size_t)N * (rt / 2 + 1) * sizeof(float4) + (size_t)rt * (N + 4) * sizeof(int64_t) + (size_t)N * sizeof(float2);
@@ -757,48 +791,90 @@ static int upload_pencil_twiddles(int lanes, int e, float2 **out) {
     return PFB_OK;
 }
 
-template <int N> static int fused_init_n(Plan *p) {
-    using Cfg = FusedCfg<N>;
+// Axis lengths of the plain fused pipeline.  Every function below that depends on a length goes through one of
+// these dispatchers, so a new length is one more case here plus an AxisCfg.
+static bool fused_axis(int n) { return n == 32 || n == 64 || n == 96 || n == 128; }
+template <int N> using IC = std::integral_constant<int, N>;
+template <class F> static int dispatch_axis(int n, F &&f) {
+    switch (n) {
+        case 32: return f(IC<32>{});
+        case 64: return f(IC<64>{});
+        case 96: return f(IC<96>{});
+        default: return f(IC<128>{});
+    }
+}
+template <class F> static int dispatch_zy(int nz, int ny, F &&f) {
+    return dispatch_axis(nz, [&](auto z) { return dispatch_axis(ny, [&](auto y) { return f(z, y); }); });
+}
+// x pencils: lanes per pencil (kernels A and C), rows per tile of the cp.async kernel C, and whether the TMA-fed
+// kernel C (8-lane swizzle arithmetic) exists for the length
+template <int N> struct XCfg {
+    static constexpr int L = AxisCfg<N>::L, RT = L == 8 ? 16 : 32;
+    static constexpr bool TMA = L == 8;
+};
+
+template <int N> static int fused_init_x(Plan *p) {
+    constexpr int TP = 33, L = XCfg<N>::L, RT = XCfg<N>::RT;
     int rc;
-    if ((rc = upload_pencil_twiddles(Cfg::LN, Cfg::EN, &p->twdN))) return rc;
-    if ((rc = upload_pencil_twiddles(Cfg::LM, Cfg::EM, &p->twdM))) return rc;
-    constexpr int TP = 33;
-    PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((rc = upload_pencil_twiddles(L, N / L, &p->twdX))) return rc;
+    PFB_CUDA(cudaFuncSetAttribute(fused_rotate_fftx_kernel<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * N * TP * sizeof(float2))));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<N>(0)));
-    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<N, (N >= 128 ? 512 : 256), true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<N>(stage_capacity<N>())));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c<N>(16)));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c_tma<N>(1)));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c_tma<N>(2)));
-    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_c_tma<N>(3)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_kernel<N, L, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_c<N>(RT)));
+    if constexpr (XCfg<N>::TMA) {
+        PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_c_tma<N>(1)));
+        PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_c_tma<N>(2)));
+        PFB_CUDA(cudaFuncSetAttribute(fused_ifftx_lcc_tma_kernel<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_c_tma<N>(3)));
+    }
     return PFB_OK;
 }
 
-bool fused_supported(int nz, int ny, int nx) { return nz == ny && ny == nx && (nx == 64 || nx == 128 || nx == 192 || nx == 256); }
+template <int NZ, int NY> static int fused_init_zy(Plan *p) {
+    using Cfg = FusedCfg<NZ, NY>;
+    int rc;
+    if ((rc = upload_pencil_twiddles(Cfg::LN, Cfg::EN, &p->twdN))) return rc;
+    if ((rc = upload_pencil_twiddles(Cfg::LM, Cfg::EM, &p->twdM))) return rc;
+    constexpr int NXC = NZ == NY ? NZ : 0;
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<NZ, NY, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b<NZ, NY>(0)));
+    PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<NZ, NY, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b<NZ, NY>(stage_capacity<NZ, NY>())));
+    if (NXC) {
+        PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<NZ, NY, NXC, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b<NZ, NY>(0)));
+        PFB_CUDA(cudaFuncSetAttribute(fused_fftyz_mul_kernel<NZ, NY, NXC, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_b<NZ, NY>(stage_capacity<NZ, NY>())));
+    }
+    return PFB_OK;
+}
+
+bool fused_supported(int nz, int ny, int nx) {
+    if (nz == ny && ny == nx && (nx == 192 || nx == 256)) return true;      // class path (fused_cls.cu)
+    return fused_axis(nz) && fused_axis(ny) && fused_axis(nx);
+}
 
 int fused_init(Plan *p) {
-    if (p->nx == 64) return fused_init_n<64>(p);
-    if (p->nx == 128) return fused_init_n<128>(p);
-    return cls_init(p);
+    if (p->cls) return cls_init(p);
+    int rc = dispatch_axis(p->nx, [&](auto nx) { return fused_init_x<decltype(nx)::value>(p); });
+    if (rc) return rc;
+    return dispatch_zy(p->nz, p->ny, [&](auto nz, auto ny) { return fused_init_zy<decltype(nz)::value, decltype(ny)::value>(p); });
 }
 
 int fused_prepare_target(Plan *p, cudaStream_t s) {
     if (p->cls) return cls_prepare_target(p, s);
-    const int N = p->nx;
-    dim3 grid(N / 32, N / 32, N / 2), block(32, 8);
+    dim3 grid(p->nx / 32, p->nz / 32, p->ny / 2), block(32, 8);
     { LaunchScope ls(p, KC_OTHER, s);
-      pair_transpose_kernel<<<grid, block, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), N); }
+      pair_transpose_kernel<<<grid, block, 0, s>>>(p->F, reinterpret_cast<float4 *>(p->Fq), p->nz, p->ny, p->nx); }
     { LaunchScope ls(p, KC_OTHER, s);
-      pair_transpose_kernel<<<grid, block, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), N); }
+      pair_transpose_kernel<<<grid, block, 0, s>>>(p->F2, reinterpret_cast<float4 *>(p->F2q), p->nz, p->ny, p->nx); }
     { LaunchScope ls(p, KC_OTHER, s);
-      const long rows = (long)N * N;
-      mask_bits_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, N, rows); }
+      const long rows = (long)p->nz * p->ny;
+      const int L = dispatch_axis(p->nx, [](auto nx) { return XCfg<decltype(nx)::value>::L; });
+      mask_bits_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, s>>>(p->lcc_mask, p->mbits, p->nx, L, rows); }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
@@ -815,7 +891,7 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
     int r2 = -1;
     PFB_CUDA(cudaMemcpyAsync(&r2, d_r2, sizeof(int), cudaMemcpyDeviceToHost, s));
     PFB_CUDA(cudaStreamSynchronize(s));
-    const int N = p->nx, rmax = N / 2;
+    const int ny = p->ny, rmax = p->rmax;
     // a rotated sample at offset r can be non-zero only if |r| <= max_r + sqrt(3)
     double reach = (r2 < 0 ? 0.0 : sqrt((double)r2)) + 1.7320508075688772 + 1e-6;
     int rs = (int)floor(reach);
@@ -825,16 +901,16 @@ int fused_prepare_template(Plan *p, cudaStream_t s) {
     p->rs2 = reach2 > (double)rmax * rmax ? rmax * rmax : (int)floor(reach2);
     if (const char *e = getenv("PFB_NO_PRUNE")) { if (atoi(e)) { p->rs = rmax; p->rs2 = rmax * rmax; } }
     unsigned ymask = 0;
-    for (int tile = 0; tile < N / 32; ++tile)
+    for (int tile = 0; tile < ny / 32; ++tile)
         for (int y = 32 * tile; y < 32 * tile + 32; ++y) {
-            const int sy = y <= N / 2 ? y : y - N;
+            const int sy = y <= ny / 2 ? y : y - ny;
             if (sy >= -p->rs && sy <= p->rs) ymask |= 1u << tile;
         }
     p->ymask = ymask;
     unsigned nmask = 0;
-    for (int y = 0; y < N; ++y) {
-        const int sy = y <= N / 2 ? y : y - N;
-        if (sy >= -p->rs && sy <= p->rs) nmask |= 1u << ((y % 64) / (N == 256 ? 4 : 8));      // ClsCfg<N>::RN
+    for (int y = 0; y < ny; ++y) {
+        const int sy = y <= ny / 2 ? y : y - ny;
+        if (sy >= -p->rs && sy <= p->rs) nmask |= 1u << ((y % 64) / (ny == 256 ? 4 : 8));      // ClsCfg<N>::RN
     }
     p->nmask = nmask;
     return PFB_OK;
@@ -845,47 +921,55 @@ template <int N, int L>
 static int fused_a_n(Plan *p, int first, int count, cudaStream_t s) {
     constexpr int TP = 33;
     const int npairs = (count + 1) / 2;
-    const int nzv = std::min(2 * p->rs + 1, N);
+    const int nzv = std::min(2 * p->rs + 1, p->nz);
     const int nyt = __builtin_popcount(p->ymask);
     LaunchScope ls(p, KC_FUSED_A, s);
     fused_rotate_fftx_kernel<N, L><<<dim3(nzv * nyt, npairs), 32 * L, 2 * N * TP * sizeof(float2), s>>>(
-        p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->ymask, nzv);
+        p->tmplq, p->mask, p->rot_dev, first, count, p->nsig, p->A, p->tw[0], p->rs, p->rs2, p->ymask, nzv, p->ny,
+        p->nz);
     return PFB_OK;
 }
 
 int launch_fused_a(Plan *p, int first, int count, cudaStream_t s) {
-    if (p->nx == 64) return fused_a_n<64, 8>(p, first, count, s);
-    return fused_a_n<128, 8>(p, first, count, s);
+    return dispatch_axis(p->nx, [&](auto nx) {
+        return fused_a_n<decltype(nx)::value, XCfg<decltype(nx)::value>::L>(p, first, count, s);
+    });
 }
 
 // kernel B of a batch: y, z, multiply, z, y out of X1 into the work buffer X2
-template <int N, int BT>
+template <int NZ, int NY>
 static int fused_b_n(Plan *p, int count, float2 *X2, cudaStream_t s) {
+    using Cfg = FusedCfg<NZ, NY>;
     const int npairs = (count + 1) / 2;
-    const int njobs = N * npairs;
-    const int grid = std::min(njobs, p->sm_count * FusedCfg<N>::CTAS);
+    const int njobs = p->nx * npairs;
+    const int grid = std::min(njobs, p->sm_count * Cfg::CTAS);
     // measured (per-kernel events, same box, three alternating repetitions): 128^3 11.96 -> 11.59 us/rotation with
     // staging, 64^3 1.64 -> 1.59
     static const int stage_env = getenv("PFB_B_STAGE") ? atoi(getenv("PFB_B_STAGE")) : 1;
     const int srows = 2 * p->rs + 2;
-    const bool staged = stage_env != 0 && 2 * p->rs + 1 < N && srows <= stage_capacity<N>();
+    const bool staged = stage_env != 0 && 2 * p->rs + 1 < NZ && srows <= stage_capacity<NZ, NY>();
     if (staged && (p->tmapB_base != (const void *)p->A || p->tmapB_rs != p->rs || p->tmapB_nsig != p->nsig)) {
-        // X1 as [pair*nsig+sig][z][kx][2N floats]; box = one whole (z, kx) row x (rs + 1) consecutive z
-        int rc = make_x1_tensor_map(&p->tmapB, p->A, 2 * N, N, N, (long)p->nsig * (p->batch / 2), p->rs + 1);
+        // X1 as [pair*nsig+sig][z][kx][2 ny floats]; box = one whole (z, kx) row x (rs + 1) consecutive z
+        int rc = make_x1_tensor_map(&p->tmapB, p->A, 2 * NY, p->nx, NZ, (long)p->nsig * (p->batch / 2), p->rs + 1);
         if (rc) return rc;
         p->tmapB_base = p->A; p->tmapB_rs = p->rs; p->tmapB_nsig = p->nsig;
     }
     LaunchScope ls(p, KC_FUSED_B, s);
-    if (staged)
-        fused_fftyz_mul_kernel<N, BT, true><<<grid, BT, smem_b<N>(srows), s>>>(
+    auto launch = [&](auto kernel, size_t smem) {
+        kernel<<<grid, Cfg::THREADS, smem, s>>>(
             reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
             reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
-            p->tw[0], p->rs, p->ymask, p->nsig, npairs, p->tmapB);
-    else
-        fused_fftyz_mul_kernel<N, BT, false><<<grid, BT, smem_b<N>(0), s>>>(
-            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
-            reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->twdN, p->twdM,
-            p->tw[0], p->rs, p->ymask, p->nsig, npairs, p->tmapB);
+            p->tw[1], p->rs, p->ymask, p->nsig, npairs, p->nx, p->tmapB);
+    };
+    constexpr int NXC = NZ == NY ? NZ : 0;
+    const bool cube = NXC != 0 && p->nx == NXC;
+    if (staged) {
+        if (cube) launch(fused_fftyz_mul_kernel<NZ, NY, NXC, true>, smem_b<NZ, NY>(srows));
+        else launch(fused_fftyz_mul_kernel<NZ, NY, 0, true>, smem_b<NZ, NY>(srows));
+    } else {
+        if (cube) launch(fused_fftyz_mul_kernel<NZ, NY, NXC, false>, smem_b<NZ, NY>(0));
+        else launch(fused_fftyz_mul_kernel<NZ, NY, 0, false>, smem_b<NZ, NY>(0));
+    }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
@@ -901,13 +985,13 @@ static int fused_back_tma(Plan *p, int first, int count, int rot_index_offset, i
                           cudaStream_t s) {
     const int npairs = (count + 1) / 2;
     if (p->tmapC_base != (const void *)X2) {
-        // X2 as [pair*3+vol][z][kx][2N floats]; box = 32 floats (8 y pairs) x all kx
-        int rc = make_x2_tensor_map(&p->tmapC, X2, 2 * N, N, N, 3L * (p->batch / 2), 32, N);
+        // X2 as [pair*3+vol][z][kx][2 ny floats]; box = 32 floats (8 y pairs) x all kx
+        int rc = make_x2_tensor_map(&p->tmapC, X2, 2 * p->ny, N, p->nz, 3L * (p->batch / 2), 32, N);
         if (rc) return rc;
         p->tmapC_base = X2;
     }
     constexpr int per_sm = NBUF == 1 ? 6 : (NBUF == 2 ? 4 : 3);
-    const int tiles = (N / 16) * N;
+    const int tiles = (p->ny / 16) * p->nz;
     // split the pair loop into chunks so that the CTAs fill whole waves of resident CTAs (a 4.6-wave launch
     // idles 8 % of the machine in its last wave); at least 8 pairs per CTA amortise its set-up and its atomics.
     // Measured at 128^3, 128 pairs: 32 pairs per chunk 4.59 us/rotation, 22 -> 4.51, 10 -> 4.52, 64 -> 5.08.
@@ -924,8 +1008,8 @@ static int fused_back_tma(Plan *p, int first, int count, int rot_index_offset, i
     if (ppc_env > 0) ppc = ppc_env;
     const int chunks = (npairs + ppc - 1) / ppc;
     LaunchScope ls(p, KC_FUSED_C, s);
-    fused_ifftx_lcc_tma_kernel<N, NBUF><<<dim3(N / 16, N, chunks), 64, smem_c_tma<N>(NBUF), s>>>(
-        p->tmapC, p->mbits, p->norm_factor, rot_index_offset + first, count, ppc, best, p->twdN);
+    fused_ifftx_lcc_tma_kernel<N, NBUF><<<dim3(p->ny / 16, p->nz, chunks), 64, smem_c_tma<N>(NBUF), s>>>(
+        p->tmapC, p->mbits, p->norm_factor, rot_index_offset + first, count, ppc, best, p->twdX, p->ny);
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
 }
@@ -935,25 +1019,27 @@ template <int N>
 static int fused_back_n(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2,
                         cudaStream_t s) {
     const int npairs = (count + 1) / 2;
-    switch (c_ring_depth()) {
-        case 1: return fused_back_tma<N, 1>(p, first, count, rot_index_offset, best, X2, s);
-        case 2: return fused_back_tma<N, 2>(p, first, count, rot_index_offset, best, X2, s);
-        case 3: return fused_back_tma<N, 3>(p, first, count, rot_index_offset, best, X2, s);
-        default: break;
+    if constexpr (XCfg<N>::TMA) {
+        switch (c_ring_depth()) {
+            case 1: return fused_back_tma<N, 1>(p, first, count, rot_index_offset, best, X2, s);
+            case 2: return fused_back_tma<N, 2>(p, first, count, rot_index_offset, best, X2, s);
+            case 3: return fused_back_tma<N, 3>(p, first, count, rot_index_offset, best, X2, s);
+            default: break;
+        }
     }
     {
         // enough CTAs for ~4 waves of resident CTAs: split the pair loop into chunks
-        const int rt = 16;
-        const int tiles = (N / rt) * N, per_sm = 96 / rt;
+        constexpr int L = XCfg<N>::L, RT = XCfg<N>::RT;
+        const int tiles = (p->ny / RT) * p->nz, per_sm = L == 8 ? 96 / RT : (N / L >= 24 ? 4 : 8);
         int chunks = std::max(1, std::min(npairs, (4 * p->sm_count * per_sm + tiles - 1) / tiles));
         int ppc = (npairs + chunks - 1) / chunks;
         static const int ppc_env = getenv("PFB_C_PPC") ? atoi(getenv("PFB_C_PPC")) : 0;
         if (ppc_env > 0) ppc = ppc_env;
         chunks = (npairs + ppc - 1) / ppc;
         LaunchScope ls(p, KC_FUSED_C, s);
-        fused_ifftx_lcc_kernel<N, 16><<<dim3(N / 16, N, chunks), 64, smem_c<N>(16), s>>>(
+        fused_ifftx_lcc_kernel<N, L, RT><<<dim3(p->ny / RT, p->nz, chunks), L * RT / 2, smem_c<N>(RT), s>>>(
             reinterpret_cast<const float4 *>(X2), p->mbits, p->norm_factor, rot_index_offset + first, count, ppc,
-            best, p->twdN);
+            best, p->twdX, p->ny, p->nz);
     }
     PFB_CUDA(cudaGetLastError());
     return PFB_OK;
@@ -966,14 +1052,16 @@ int fused_a(Plan *p, int first, int count, cudaStream_t s) {
 
 int fused_b(Plan *p, int count, float2 *X2, cudaStream_t s) {
     if (p->cls) return cls_b(p, count, X2, s);
-    if (p->nx == 64) return fused_b_n<64, 256>(p, count, X2, s);
-    return fused_b_n<128, 512>(p, count, X2, s);
+    return dispatch_zy(p->nz, p->ny, [&](auto nz, auto ny) {
+        return fused_b_n<decltype(nz)::value, decltype(ny)::value>(p, count, X2, s);
+    });
 }
 
 int fused_c(Plan *p, int first, int count, int rot_index_offset, int64_t *best, const float2 *X2, cudaStream_t s) {
     if (p->cls) return cls_c(p, first, count, rot_index_offset, best, X2, s);
-    if (p->nx == 64) return fused_back_n<64>(p, first, count, rot_index_offset, best, X2, s);
-    return fused_back_n<128>(p, first, count, rot_index_offset, best, X2, s);
+    return dispatch_axis(p->nx, [&](auto nx) {
+        return fused_back_n<decltype(nx)::value>(p, first, count, rot_index_offset, best, X2, s);
+    });
 }
 
 // The whole rotation list, batch by batch.  Kernel A of batch i+1 (gather-latency bound, writes X1) runs on a

@@ -5,6 +5,7 @@
 #include "fft_core.cuh"
 
 #include <cmath>
+#include <type_traits>
 
 namespace pfb {
 
@@ -92,15 +93,24 @@ extern "C" int pfb_pencil_fft(int kind, int lanes, int e, const float *in, float
     const float4 *i4 = reinterpret_cast<const float4 *>(in);
     float4 *o4 = reinterpret_cast<float4 *>(out);
     if (kind == 3) {
-        PFB_REQUIRE(lanes == 8 && (e == 8 || e == 16), "pfb_pencil_fft: scalar pencils are 8 x 8 or 8 x 16");
-        constexpr size_t sm8 = 4 * 64 * sizeof(float4) + 2 * 64 * sizeof(float2), sm16 = 4 * 128 * sizeof(float4) + 2 * 128 * sizeof(float2);
-        if (e == 8) pencil_op_kernel<8, 8, 3><<<(count + 3) / 4, 32, sm8, s>>>(i4, o4, count);
-        else pencil_op_kernel<8, 16, 3><<<(count + 3) / 4, 32, sm16, s>>>(i4, o4, count);
+        // kernel A's scalar pencils: 8 x 8 (64), 8 x 16 (128), 4 x 8 (32), 4 x 24 (96)
+        auto scalar = [&](auto lt, auto et) {
+            constexpr int L = decltype(lt)::value, E = decltype(et)::value, N = L * E, G = 32 / L;
+            pencil_op_kernel<L, E, 3><<<(count + G - 1) / G, 32, G * N * sizeof(float4) + 2 * N * sizeof(float2), s>>>(i4, o4, count);
+        };
+        if (lanes == 8 && e == 8) scalar(std::integral_constant<int, 8>{}, std::integral_constant<int, 8>{});
+        else if (lanes == 8 && e == 16) scalar(std::integral_constant<int, 8>{}, std::integral_constant<int, 16>{});
+        else if (lanes == 4 && e == 8) scalar(std::integral_constant<int, 4>{}, std::integral_constant<int, 8>{});
+        else if (lanes == 4 && e == 24) scalar(std::integral_constant<int, 4>{}, std::integral_constant<int, 24>{});
+        else { set_error("pfb_pencil_fft: scalar pencils are 8 x 8, 8 x 16, 4 x 8 or 4 x 24"); return PFB_ERR_INVALID; }
         PFB_CUDA(cudaGetLastError());
         return PFB_OK;
     }
     // the (lanes, points per lane) pairs the search kernels use
-    if (lanes == 4 && e == 8) return launch_pencil_op<4, 8>(kind, i4, o4, count, s);      // 64-point rows (packed 32)
+    if (lanes == 4 && e == 4) return launch_pencil_op<4, 4>(kind, i4, o4, count, s);      // 32-point rows (packed 16)
+    if (lanes == 4 && e == 8) return launch_pencil_op<4, 8>(kind, i4, o4, count, s);      // 32-point pencils, 64-point rows (packed 32)
+    if (lanes == 4 && e == 12) return launch_pencil_op<4, 12>(kind, i4, o4, count, s);    // 96-point rows (packed 48)
+    if (lanes == 4 && e == 24) return launch_pencil_op<4, 24>(kind, i4, o4, count, s);    // 96-point pencils
     if (lanes == 8 && e == 8) return launch_pencil_op<8, 8>(kind, i4, o4, count, s);      // 64-point pencils, 128-point rows
     if (lanes == 8 && e == 16) return launch_pencil_op<8, 16>(kind, i4, o4, count, s);    // 128-point pencils
     if (lanes == 8 && e == 24) return launch_pencil_op<8, 24>(kind, i4, o4, count, s);    // 192-point pencils

@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import pyramid
-from .correlator import fused_cube
+from .correlator import fused_shape
 
 
 def is_multiple2357(num):                              # volume.py:111-118
@@ -55,7 +55,9 @@ def extend(array, shape):
 def prepare_target(array, voxelspacing, origin, resolution, resampling_rate=2, no_resampling=False,
                    no_trimming=False, trimming_cutoff=None, fused=False, device=None):
     """powerfit.py:219-233.  Returns (array, voxelspacing, origin).  ``fused=True`` extends to the next
-    cubic grid with a fused pipeline (64/128/192/256) instead of the next 2.3.5.7-smooth shape."""
+    grid with a fused pipeline (every axis up to 32/64/96/128; 192^3 / 256^3 beyond) instead of the next
+    2.3.5.7-smooth shape -- a legitimate choice of the CLI's `extend` size, so the search result is what the reference
+    computes on the same extended map."""
     array = np.asarray(array, dtype=np.float64)
     origin = list(origin)
     if not no_resampling:
@@ -68,7 +70,7 @@ def prepare_target(array, voxelspacing, origin, resolution, resampling_rate=2, n
         array, origin = trim(array, voxelspacing, origin, trimming_cutoff)
     shape = [nearest_multiple2357(n) for n in array.shape]
     if fused:
-        n = fused_cube(shape)
+        n = fused_shape(shape)
         if n is not None:
-            shape = [n, n, n]
+            shape = list(n)
     return extend(array, shape), voxelspacing, origin

@@ -33,7 +33,14 @@ def golden_inputs(g, name):
     if "target" in g.files:
         return (g["target"].astype(np.float64), g["template"].astype(np.float64),
                 g["mask"].astype(np.float64))
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    if "case_kwargs" in g.files:
+        import json
+        kw = json.loads(str(g["case_kwargs"]))
+        if "shape" in kw:
+            kw["shape"] = tuple(kw["shape"])
+        case = synth.make_case(**kw)
+        return f32(case.target), f32(case.template), f32(case.mask)
     cw = "cw" in name
     case = synth.config2(seed=int(g["seed"]), core_weighted=cw)
-    f32 = lambda a: a.astype(np.float32).astype(np.float64)
     return f32(case.target), f32(case.template), f32(case.mask)

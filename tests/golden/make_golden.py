@@ -153,6 +153,22 @@ def scans():
               extra=dict(subset_index=idx, seed=np.array(0)))
 
 
+def scans_mixed():
+    """CLI-like non-cubic grids whose axes are fused lengths (32 / 64 / 96 / 128): they take the per-axis fused
+    pipeline.  Inputs are regenerated from the seeded generator (the keyword arguments travel in the file)."""
+    import json
+    full = rotation_set(20.0)
+    for name, kw, laplace, nrot in [
+            ("scan_96x128x64_laplace", dict(shape=(96, 128, 64), voxelspacing=3.0, resolution=9.0, n_res=150, rg=11.0,
+                                            n_copies=3, seed=31), True, 14),
+            ("scan_32x64x96_cw", dict(shape=(32, 64, 96), voxelspacing=3.0, resolution=9.0, n_res=50, rg=5.5,
+                                      n_copies=3, seed=32, core_weighted=True), False, 15)]:
+        idx = np.unique(np.r_[np.arange(0, len(full), len(full) // (nrot - 1))[:nrot - 1], len(full) - 1])
+        case = synth.make_case(**kw)
+        save_scan(name, case, full[idx], laplace, store_inputs=False,
+                  extra=dict(subset_index=idx, case_kwargs=np.array(json.dumps(kw))))
+
+
 def scan_256():
     """BASELINE config 4 (subset): 256^3, Laplace + core-weighted, 6 rotations of the 4.71 deg set + 2 true poses.
     Only eight z planes of the result grids are stored (the full grids would be 200 MB)."""
@@ -212,9 +228,12 @@ if __name__ == "__main__":
         scan_256()
     elif len(sys.argv) > 1 and sys.argv[1] == "192":
         scan_192()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mixed":
+        scans_mixed()
     else:
         rotate_vectors()
         lcc_chain()
         scans()
+        scans_mixed()
         scan_256()
         scan_192()

@@ -99,7 +99,7 @@ def test_fft3_matches_numpy(pfb, shape):
     assert np.abs(out - ref).max() / scale < 2e-6
 
 
-@pytest.mark.parametrize("lanes,e", [(4, 8), (8, 8), (8, 16), (8, 24), (16, 16)])
+@pytest.mark.parametrize("lanes,e", [(4, 4), (4, 8), (4, 12), (4, 24), (8, 8), (8, 16), (8, 24), (16, 16)])
 def test_fused_pencil_building_blocks_match_numpy(pfb, lanes, e):
     """Operator-level pin of the register / shared-memory FFT blocks the fused kernels are made of
     (csrc/fft_core.cuh through pfb_pencil_fft): packed pencils, both row transforms with the split radix-2 step,
@@ -134,7 +134,7 @@ def test_fused_pencil_building_blocks_match_numpy(pfb, lanes, e):
     assert np.abs(lo - X[:, :n]).max() < tol(X) and np.abs(hi - X[:, n:]).max() < tol(X)
     ev, od = unpack(run(2, pack(x[:, :n], x[:, n:])))                              # split in -> (X[2k], X[2k+1])
     assert np.abs(ev - X[:, 0::2]).max() < tol(X) and np.abs(od - X[:, 1::2]).max() < tol(X)
-    if lanes == 8 and e in (8, 16):                                                # kernel A's scalar pencil
+    if (lanes, e) in ((8, 8), (8, 16), (4, 8), (4, 24)):                           # kernel A's scalar pencils
         o = run(3, np.stack([a.real, a.imag, 0 * a.real, 0 * a.real], axis=-1))    # scalar: float4 = (re, im, -, -)
         assert np.abs(o[..., 0] + 1j * o[..., 1] - dft(a)).max() < tol(dft(a))
 
@@ -462,23 +462,27 @@ def test_multi_template_slots_equal_fresh_correlators(pfb, oracle):
             m.select(len(cases))
 
 
-def test_padding_to_a_fused_cube(pfb):
-    """pad=True: an arbitrary (CLI-like) shape is searched on the next fused cube; the result equals the
-    search on explicitly padded inputs exactly, and the unpadded any-shape search away from the box faces."""
+def test_padding_to_a_fused_grid(pfb):
+    """pad=True: an arbitrary (CLI-like) shape is searched on the next fused grid (every axis rounded up to 32 / 64 /
+    96 / 128); the result equals the search on explicitly padded inputs exactly, and the unpadded any-shape search
+    away from the box faces."""
     from powerfit_b200 import synth
-    from powerfit_b200.correlator import pad_target, pad_wrapped
-    shape = (40, 50, 42)
-    case = synth.make_case(shape=shape, voxelspacing=3.0, resolution=9.0, n_res=60, rg=8.0, n_copies=2, seed=51)
+    from powerfit_b200.correlator import pad_target, pad_wrapped, fused_shape
+    shape = (40, 70, 28)
+    big = fused_shape(shape)
+    assert big == (64, 96, 32)
+    case = synth.make_case(shape=shape, voxelspacing=3.0, resolution=9.0, n_res=40, rg=6.0, n_copies=2, seed=51)
     rots = synth.random_rotations(9, seed=5)
     c = pfb.CUDACorrelator(case.target, laplace=False, pad=True)
     c.template, c.mask, c.rotations = case.template, case.mask, rots
     c.scan()
     assert c.plan_info(6) == 1 and c.lcc.shape == shape and c.rot.shape == shape
-    e = run_scan(pfb, pad_target(case.target, 64), pad_wrapped(case.template, 64), pad_wrapped(case.mask, 64), rots, False)
-    assert np.array_equal(c.lcc, e.lcc[:40, :50, :42]) and np.array_equal(c.rot, e.rot[:40, :50, :42])
+    e = run_scan(pfb, pad_target(case.target, big), pad_wrapped(case.template, big), pad_wrapped(case.mask, big), rots, False)
+    assert e.plan_info(6) == 1
+    assert np.array_equal(c.lcc, e.lcc[:40, :70, :28]) and np.array_equal(c.rot, e.rot[:40, :70, :28])
     g = run_scan(pfb, case.target, case.template, case.mask, rots, False)          # any-shape pipeline, periodic box
     assert g.plan_info(6) == 0
-    inner = (slice(12, 28), slice(12, 38), slice(12, 30))
+    inner = (slice(10, 30), slice(10, 60), slice(10, 18))
     assert np.abs(c.lcc[inner] - g.lcc[inner]).max() < 1e-4
 
 
@@ -551,6 +555,55 @@ def test_fused_path_equals_generic_path(pfb, monkeypatch, n, cw, laplace):
         assert np.abs(lcc - g_lcc)[~same].max(initial=0) < 2e-5
     assert np.array_equal(results["fused"][0], results["fused_noprune"][0])
     assert np.array_equal(results["fused"][1], results["fused_noprune"][1])
+
+
+MIXED = [((64, 128, 64), False, False), ((128, 64, 128), True, True), ((64, 64, 128), True, False),
+         ((128, 128, 64), False, True), ((96, 128, 64), False, False), ((32, 96, 96), True, True),
+         ((96, 96, 96), False, True), ((32, 32, 32), True, False), ((128, 32, 96), False, False),
+         ((64, 96, 32), True, True), ((32, 64, 128), False, True), ((96, 32, 64), True, False)]
+
+
+@pytest.mark.parametrize("shape,cw,laplace", MIXED)
+def test_mixed_axis_fused_path_equals_generic_path(pfb, monkeypatch, shape, cw, laplace):
+    """Per-axis fused pipeline (any mix of 32 / 64 / 96 / 128 voxels per axis: 4-lane and 8-lane pencils, radix-3
+    register DFTs at 96, with and without the TMEM stash / TMA staging / TMA-fed kernel C) against the any-shape
+    generic pipeline on the same inputs, with and without support pruning, odd rotation count."""
+    from powerfit_b200 import synth
+    small = min(shape)
+    case = synth.make_case(shape=shape, voxelspacing=3.0, resolution=9.0, n_res=40 if small == 32 else 120,
+                           rg=5.0 if small == 32 else 10.0, n_copies=3, seed=sum(shape), core_weighted=cw)
+    rots = synth.random_rotations(7, seed=4)
+    results = {}
+    for mode, env in [("generic", {"PFB_FUSED": "0"}), ("fused", {"PFB_FUSED": "1"}),
+                      ("fused_noprune", {"PFB_FUSED": "1", "PFB_NO_PRUNE": "1"})]:
+        for k in ("PFB_FUSED", "PFB_NO_PRUNE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = run_scan(pfb, case.target, case.template, case.mask, rots, laplace, batch=4)
+        assert c.plan_info(6) == (0 if mode == "generic" else 1)
+        results[mode] = (c.lcc.copy(), c.rot.copy())
+    g_lcc, g_rot = results["generic"]
+    assert (g_lcc > 0).sum() > 100
+    for mode in ("fused", "fused_noprune"):
+        lcc, rot = results[mode]
+        assert np.abs(lcc - g_lcc).max() < 2e-5, mode
+        same = rot == g_rot
+        assert same.mean() > 0.999, (mode, same.mean())
+        assert np.abs(lcc - g_lcc)[~same].max(initial=0) < 2e-5
+    assert np.array_equal(results["fused"][0], results["fused_noprune"][0])
+    assert np.array_equal(results["fused"][1], results["fused_noprune"][1])
+
+
+@pytest.mark.parametrize("name", ["scan_96x128x64_laplace", "scan_32x64x96_cw"])
+def test_scan_mixed_axis_golden(pfb, name):
+    """Reference CPU search (real reference, tests/golden/make_golden.py) on CLI-like non-cubic grids that take the
+    per-axis fused pipeline."""
+    g = load_golden(name)
+    target, template, mask = golden_inputs(g, name)
+    c = run_scan(pfb, target, template, mask, g["rotations"], bool(g["laplace"]))
+    assert c.plan_info(6) == 1
+    check_against_golden(c, g)
 
 
 @pytest.mark.parametrize("n,cw,laplace,count", [(256, True, True, 5), (256, False, False, 4), (192, True, True, 5),
@@ -762,7 +815,7 @@ def test_target_prep_matches_reference_golden(pfb):
     assert arr.shape == ref.shape and vs == float(g["final_vs"]) and np.allclose(origin, g["trim_origin"], rtol=0, atol=0)
     assert np.abs(arr - ref).max() <= 4 * np.finfo(np.float64).eps * np.abs(ref).max()
     cube, _, _ = T.prepare_target(g["map"], float(g["voxelspacing"]), list(g["origin"]), float(g["resolution"]), fused=True)
-    assert cube.shape == (64, 64, 64) and np.array_equal(cube[:ref.shape[0], :ref.shape[1], :ref.shape[2]], arr)
+    assert cube.shape == (32, 32, 32) and np.array_equal(cube[:ref.shape[0], :ref.shape[1], :ref.shape[2]], arr)
 
 
 def test_map_file_to_search(pfb, tmp_path):

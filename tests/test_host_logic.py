@@ -155,7 +155,7 @@ def test_laplace_operation_order_is_scipys():
 
 def test_wrapped_padding_preserves_offsets():
     """pad_wrapped keeps every voxel at its signed offset from voxel 0 (the template's centre)."""
-    from powerfit_b200.correlator import pad_wrapped, pad_target, fused_cube
+    from powerfit_b200.correlator import pad_wrapped, pad_target, fused_cube, fused_shape
     rng = np.random.default_rng(3)
     a = rng.random((10, 13, 9))
     p = pad_wrapped(a, 64)
@@ -166,6 +166,16 @@ def test_wrapped_padding_preserves_offsets():
     t = pad_target(a, 64)
     assert np.array_equal(t[:10, :13, :9], a) and t.sum() == a.sum()
     assert fused_cube((40, 52, 46)) == 64 and fused_cube((100, 90, 84)) == 128 and fused_cube((300, 10, 10)) is None
+    # per-axis padding: every axis to the next of 32 / 64 / 96 / 128, cubes beyond
+    assert fused_shape((28, 40, 27)) == (32, 64, 32) and fused_shape((96, 128, 64)) == (96, 128, 64)
+    assert fused_shape((100, 90, 84)) == (128, 96, 96) and fused_shape((130, 20, 20)) == (192, 192, 192)
+    assert fused_shape((200, 256, 31)) == (256, 256, 256) and fused_shape((300, 10, 10)) is None
+    q = pad_wrapped(a, (32, 64, 32))
+    assert q.shape == (32, 64, 32) and q.sum() == a.sum()
+    for idx in [(0, 0, 0), (3, 6, 4), (9, 12, 8), (5, 7, 5), (6, 6, 4)]:
+        off = [i if i <= s // 2 else i - s for i, s in zip(idx, a.shape)]
+        assert q[tuple(o % n for o, n in zip(off, q.shape))] == a[idx]
+    assert pad_target(a, (32, 64, 32)).shape == (32, 64, 32)
 
 
 def test_bench_reference_arm_contract():

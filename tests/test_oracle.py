@@ -124,7 +124,8 @@ def test_contract_errors(oracle):
         c.rotations = [0] * 3
 
 
-SMALL = ["scan_16x18x20_plain", "scan_12x15x14_laplace", "scan_24_laplace_cw", "scan_32_plain"]
+SMALL = ["scan_16x18x20_plain", "scan_12x15x14_laplace", "scan_24_laplace_cw", "scan_32_plain", "scan_32x64x96_cw",
+         "scan_96x128x64_laplace"]
 
 
 @pytest.mark.parametrize("name", SMALL)
