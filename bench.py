@@ -46,7 +46,21 @@ WORKLOADS = {
                     desc="synthetic 192^3 map @8A, one of 4 sub-unit templates, 2.5deg search, plain LCC"),
     "config4": dict(n=256, laplace=True, cw=True, angle="4.71deg", full_R=70728,
                     desc="ribosome-sized synthetic 256^3 map @6A, 4.71deg search, Laplace + core-weighted"),
+    # not a BASELINE config: a non-cubic grid of the kind the reference CLI's trim + extend produces, on the per-axis
+    # fused pipeline (the input of tests/golden/scan_96x128x64_laplace.npz)
+    "cli_96x128x64": dict(n=128, shape=(96, 128, 64), laplace=True, cw=False, angle="20deg", full_R=648,
+                          desc="synthetic 96x128x64 map @9A (a CLI-like trimmed + extended grid), Laplace"),
 }
+
+
+def shape_of(w):
+    return tuple(w.get("shape", (w["n"],) * 3))
+
+
+def spectrum_bytes(w):
+    """S of SURVEY 8(d): one complex64 half-spectrum."""
+    nz, ny, nx = shape_of(w)
+    return 8 * nz * ny * (nx // 2 + 1)
 
 
 def make_inputs(workload):
@@ -58,6 +72,8 @@ def make_inputs(workload):
         case = synth.config4(seed=0)
     elif workload == "config5":
         case = synth.config5(seed=0)
+    elif workload == "cli_96x128x64":
+        case = synth.make_case(shape=(96, 128, 64), voxelspacing=3.0, resolution=9.0, n_res=150, rg=11.0, n_copies=3, seed=31)
     else:
         case = synth.config2(seed=0, core_weighted=w["cw"])
     return case
@@ -76,26 +92,27 @@ def search_rotations(workload, count):
     return synth.random_rotations(count, seed=1), "seeded uniform random rotations"
 
 
-def default_batch(n):
+def default_batch(w):
     """pfb_plan_create's default rotations per batch (csrc/api.cu)."""
-    per_pair = 6 * n ** 3 * 8
+    per_pair = 6 * int(np.prod(shape_of(w))) * 8
     pairs = max(1, min(256, (32768 << 20) // per_pair))
     return 2 * pairs
 
 
 def workload_config(w, world, rps, batch, rot_desc):
     """The `config` object both arms print (the reference arm times a bounded sample of this workload)."""
-    n = w["n"]
     nf = 3 if w["cw"] else 2
-    return {"workload": w["desc"], "shape": [n, n, n], "rotations_per_step_per_gpu": int(rps), "rotation_set": rot_desc,
+    return {"workload": w["desc"], "shape": list(shape_of(w)), "rotations_per_step_per_gpu": int(rps), "rotation_set": rot_desc,
             "batch": int(batch), "mask": "core-weighted" if w["cw"] else "binary", "laplace": w["laplace"],
             "parallelism": "rotation shards x%d + packed MAX all-reduce" % world,
             "l2": "working set per batch (%.0f MB) exceeds the 126 MB L2; no flush needed"
-                  % (batch / 2 * (nf + 3) * 8 * n ** 3 / 1e6)}
+                  % (batch / 2 * (nf + 3) * 8 * int(np.prod(shape_of(w))) / 1e6)}
 
 
 def default_rps(w):
     n = w["n"]
+    if "shape" in w:
+        return 4096
     # one step = one full rotational search of the named angle at 128^3 (7416 rotations); bounded blocks elsewhere
     return {64: 2048, 128: w["full_R"], 256: 128, 192: 150}.get(n, 256)
 
@@ -267,7 +284,7 @@ def run_reference(args, w, rank, world, emit):
     out = {"impl": "reference", "metric": "rotations/s (LCC search)", "value": val, "unit": "rotations/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(w, world, args.rot_per_step or default_rps(w), args.batch or default_batch(n), rot_desc),
+           "config": workload_config(w, world, args.rot_per_step or default_rps(w), args.batch or default_batch(w), rot_desc),
            "cpu_baseline": {"value": val, "unit": "rotations/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
            "e2e": {"value": val, "unit": "rotations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -428,14 +445,13 @@ def extra_config(workload, dev, steps=2, warmup=1):
     import torch
     from powerfit_b200 import CUDACorrelator, _lib
     w = WORKLOADS[workload]
-    n = w["n"]
     case = make_inputs(workload)
     rps = default_rps(w)
     rots, rot_desc = search_rotations(workload, rps * (steps + warmup))
     corr = CUDACorrelator(case.target, device=dev, laplace=w["laplace"])
     corr.template, corr.mask, corr.rotations = case.template, case.mask, rots
     nf = 2 if corr._mask_binary else 3
-    S = 8 * n * n * (n // 2 + 1)
+    S = spectrum_bytes(w)
     stream = torch.cuda.current_stream(dev)
     for i in range(warmup):
         corr.scan_device(i * rps, (i + 1) * rps, reset=(i == 0))
@@ -451,6 +467,7 @@ def extra_config(workload, dev, steps=2, warmup=1):
     peak, _ = peak_hbm()
     kern = kernel_split(corr, _lib.load(), lambda: corr.scan_device(0, rps, reset=False))
     out = {"workload": w["desc"], "rotations_per_step": rps, "steps": steps, "warmup": warmup, "rotation_set": rot_desc,
+           "shape": list(shape_of(w)), "fused": int(corr.plan_info(6)),
            "value": value, "unit": "rotations/s", "batch": corr.plan_info(4), "mask": "binary" if nf == 2 else "core-weighted",
            "bytes_per_rotation": (2 * nf + 6) * S, "step_frac": value * (2 * nf + 6) * S / 1e9 / peak,
            "us_per_rotation": {k: 1e3 * v["ms"] / rps for k, v in kern.items()}}
@@ -512,7 +529,7 @@ def main():
 
     case = make_inputs(args.workload)
     n = w["n"]
-    V = n ** 3
+    V = int(np.prod(shape_of(w)))
     rps = args.rot_per_step or default_rps(w)
     total_steps = args.warmup + args.steps
     rots, rot_desc = search_rotations(args.workload, rps * total_steps * world + 8)
@@ -522,7 +539,7 @@ def main():
     corr.mask = case.mask
     corr.rotations = rots
     nf = 2 if corr._mask_binary else 3
-    S = 8 * n * n * (n // 2 + 1)
+    S = spectrum_bytes(w)
     B_rot = (2 * nf + 6) * S
     stream = torch.cuda.current_stream(dev)
 
@@ -657,7 +674,7 @@ def main():
     # ---------------- the other BASELINE configs, measured in this process (N = 1 only)
     others = {}
     if world == 1 and not args.no_extras:
-        for name in ("config1", "config3", "config5", "config4"):
+        for name in ("config1", "config3", "config5", "config4", "cli_96x128x64"):
             if name == args.workload:
                 continue
             try:
