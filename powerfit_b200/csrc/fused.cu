@@ -72,22 +72,33 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
         tile_m[idx] = make_float2(0.f, 0.f);
     }
     __syncthreads();
-    const int xlo = max(-rs, -(N / 2 - 1)), W = rs - xlo + 1;
+    const int xlo = max(-rs, -(N / 2 - 1));
     const int lim2 = min(rs2, rmax * rmax);
     // both rotations of a position are fetched before either is blended (six gathers in flight); an odd
-    // last pair samples rotation a twice and discards the copy
+    // last pair samples rotation a twice and discards the copy.
+    // Rows are dealt to groups of LPR lanes; a group walks only the x span of its row that lies inside the
+    // sphere (every lane of a busy group has a sample), with the (z, y) part of the source coordinate -- the
+    // reference's per-row partial sums -- computed once per row.
     const double *Rb2 = have_b ? Rb : Ra;
-    for (int idx = threadIdx.x; idx < 32 * W; idx += THREADS) {
-        const int r = idx / W, ox = idx % W + xlo;
-        const int iy = y0 + r;
-        const int oy = iy <= ny / 2 ? iy : iy - ny;
-        if (ox * ox + oy * oy + oz * oz <= lim2) {
-            const SrcCoord ca = source_coord(Ra, ox, oy, oz), cb = source_coord(Rb2, ox, oy, oz);
-            const float ta = sample_trilinear_q(tmplq, d, ca), tb = sample_trilinear_q(tmplq, d, cb);
-            const float ma = sample_nearest(mask, d, ca), mb = sample_nearest(mask, d, cb);
-            const int x = ox < 0 ? ox + N : ox;
-            tile_t[x * TP + r] = make_float2(ta, have_b ? tb : 0.f);
-            tile_m[x * TP + r] = make_float2(ma, have_b ? mb : 0.f);
+    {
+        constexpr int LPR = 16, GROUPS = THREADS / LPR;
+        const int gl = threadIdx.x % LPR;
+        for (int r = threadIdx.x / LPR; r < 32; r += GROUPS) {
+            const int iy = y0 + r;
+            const int oy = iy <= ny / 2 ? iy : iy - ny;
+            const int rem = lim2 - oy * oy - oz * oz;
+            if (rem < 0) continue;
+            const int hw = isqrt_floor(rem);
+            const int lo = max(xlo, -hw), hi = min(rs, hw);
+            const SrcCoord rowa = source_row(Ra, oy, oz), rowb = source_row(Rb2, oy, oz);
+            for (int ox = lo + gl; ox <= hi; ox += LPR) {
+                const SrcCoord ca = source_in_row(rowa, Ra, ox), cb = source_in_row(rowb, Rb2, ox);
+                const float ta = sample_trilinear_q(tmplq, d, ca), tb = sample_trilinear_q(tmplq, d, cb);
+                const float ma = sample_nearest(mask, d, ca), mb = sample_nearest(mask, d, cb);
+                const int x = ox < 0 ? ox + N : ox;
+                tile_t[x * TP + r] = make_float2(ta, have_b ? tb : 0.f);
+                tile_m[x * TP + r] = make_float2(ma, have_b ? mb : 0.f);
+            }
         }
     }
     __syncthreads();

@@ -32,6 +32,30 @@ __device__ __forceinline__ SrcCoord source_coord(const double *__restrict__ R, i
     return c;
 }
 
+// The same sums with the (z, y) part of a row computed once: row = (R6 z + R3 y, R7 z + R4 y, R8 z + R5 y), then
+// + R0..2 x per sample -- the reference's own loop nest (_extensions.c:60-89), identical roundings.
+__device__ __forceinline__ SrcCoord source_row(const double *__restrict__ R, int y, int z) {
+    SrcCoord c;
+    c.x = __dadd_rn(__dmul_rn(R[6], (double)z), __dmul_rn(R[3], (double)y));
+    c.y = __dadd_rn(__dmul_rn(R[7], (double)z), __dmul_rn(R[4], (double)y));
+    c.z = __dadd_rn(__dmul_rn(R[8], (double)z), __dmul_rn(R[5], (double)y));
+    return c;
+}
+__device__ __forceinline__ SrcCoord source_in_row(const SrcCoord &row, const double *__restrict__ R, int x) {
+    SrcCoord c;
+    c.x = __dadd_rn(row.x, __dmul_rn(R[0], (double)x));
+    c.y = __dadd_rn(row.y, __dmul_rn(R[1], (double)x));
+    c.z = __dadd_rn(row.z, __dmul_rn(R[2], (double)x));
+    return c;
+}
+// largest h >= 0 with h*h <= v (v >= 0)
+__device__ __forceinline__ int isqrt_floor(int v) {
+    int h = (int)sqrtf((float)v);
+    while (h * h > v) --h;
+    while ((h + 1) * (h + 1) <= v) ++h;
+    return h;
+}
+
 __device__ __forceinline__ float sample_nearest(const float *__restrict__ g, const GridDims &d, const SrcCoord &c) {
     const int i = wrap_index((int)round(c.x), d.nx);
     const int j = wrap_index((int)round(c.y), d.ny);

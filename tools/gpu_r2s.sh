@@ -1,0 +1,13 @@
+#!/bin/bash
+# kernel A: row-wise gather (sphere-restricted x spans), 2 vs 3 CTAs per SM in the class path
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "fused_path or class_path or mixed or golden" 2>&1 | tail -4
+show='
+import json,sys
+d=json.loads(sys.stdin.read()); print(sys.argv[1], "rot/s %.0f  e2e %.0f  frac %.3f" % (d["value"], d["e2e"]["value"], d["roofline"]["step_frac"]), {k: round(v["us_per_rotation"],2) for k,v in d["roofline"]["kernels"].items()})'
+for w in config2 config1; do
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --workload $w 2>gpurun_out/err_$w.txt | python -c "$show" $w
+done
+for ct in 2 3; do for w in config4 config5; do
+PFB_A_CTAS=$ct timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --workload $w 2>gpurun_out/err_$w.txt | python -c "$show" "$w ctas=$ct"
+done; done
