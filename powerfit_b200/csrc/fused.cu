@@ -67,10 +67,9 @@ fused_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restri
     // ---- gather the 32 x N tile of both signals (zeros outside the sphere / support)
     //      zero-fill first, then visit only the x offsets inside the support box [xlo, rs];
     //      offset -N/2 is skipped: it aliases index N/2, which belongs to offset +N/2.
-    for (int idx = threadIdx.x; idx < N * TP; idx += THREADS) {
-        tile_t[idx] = make_float2(0.f, 0.f);
-        tile_m[idx] = make_float2(0.f, 0.f);
-    }
+    // both tiles are one contiguous run of 2 N TP float2 (an even count): 16-byte stores
+    for (int idx = threadIdx.x; idx < N * TP; idx += THREADS)
+        reinterpret_cast<float4 *>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const int xlo = max(-rs, -(N / 2 - 1));
     const int lim2 = min(rs2, rmax * rmax);

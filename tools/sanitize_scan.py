@@ -5,7 +5,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from powerfit_b200 import CUDACorrelator, shapes, synth
 
-sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256]
+# arguments: cube edges, or shapes as ZxYxX (per-axis fused pipeline); "-b" after a shape: binary mask
+args = sys.argv[1:] or ["64", "128", "256"]
+for a in args:
+    if "x" in a:
+        binary = a.endswith("b")
+        shape = tuple(int(v) for v in a.rstrip("b").split("x"))
+        small = min(shape) == 32
+        case = synth.make_case(shape=shape, voxelspacing=3.0, resolution=9.0, n_res=40 if small else 120,
+                               rg=5.0 if small else 10.0, n_copies=2, seed=3, core_weighted=not binary)
+        c = CUDACorrelator(case.target, laplace=True, batch=4)
+        c.template, c.mask, c.rotations = case.template, case.mask, synth.random_rotations(5, seed=2)
+        c.scan()
+        print(a, "fused", c.plan_info(6), "class", c.plan_info(9), "max lcc %.4f" % c.lcc.max(), flush=True)
+sizes = [int(a) for a in args if "x" not in a]
 for n in sizes:
     case = synth.make_case(n=n, voxelspacing=2.8, resolution=9.0, n_res=120, rg=11.0, n_copies=2, seed=3,
                            core_weighted=(n not in (128, 192)))      # 128 / 192: binary mask -> TMEM spectrum stash
