@@ -181,12 +181,17 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
 // phase 1 and no forward z.
 // Tile layout: plane[z][c], c < 32, float4 = columns (k' = c, c + 32) in split form.
 // (256^3: 256 threads at 232 registers; 512 threads at 128 registers measured 138 -> 158 us per rotation)
-template <int N>
+// STAGED (as in fused_fftyz_mul_kernel): the support rows of the CTA's next forward plane -- 512 bytes per z of its
+// class -- are copied by TMA into a staging area behind the tile while phase 2 runs, two 4-D boxes (rows z = 0..rs
+// and z = N-rs..N-1) issued by one thread; the row loop then reads them from shared memory instead of waiting for
+// an L2 round trip per row with eight resident warps (17 % of the stall samples at 256^3,
+// profiles/r02_ncu_v4_cls_256.txt).  Used when the staging area fits next to the tile (2 rs + 2 rows).
+template <int N, bool STAGED>
 __global__ void __launch_bounds__(ClsCfg<N>::THREADS, ClsCfg<N>::CTAS)
 cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, const float4 *__restrict__ Fc,
                      const float4 *__restrict__ F2c, const float2 *__restrict__ twN_g,
                      const float2 *__restrict__ twM_g, const float2 *__restrict__ twh_g,
-                     int rs, unsigned nmask, int nsig, int npairs) {
+                     int rs, unsigned nmask, int nsig, int npairs, const __grid_constant__ CUtensorMap tmapX1) {
     using Cfg = ClsCfg<N>;
     constexpr int H = N / 2, HC = 32, P = 33, NB = Cfg::NB, PPT = Cfg::PPT;
     constexpr int LN = Cfg::LN, EN = Cfg::EN, GN = 32 / LN;      // column pencils: N points
@@ -202,6 +207,9 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
     float2 *twM = twN + N;                                        // [EM][LM] W_32^(t k1)
     float2 *twh_s = twM + 32;                                     // [32] W_64^k of the split radix-2 step
     uint32_t *tslot = reinterpret_cast<uint32_t *>(twh_s + 32);
+    uint64_t *sbar = reinterpret_cast<uint64_t *>(tslot + 2);     // staging copies have landed
+    // staging rows: zi = z for z <= rs, zi = rs + 1 + (z - (N - rs)) for the rows below zero; 128-byte aligned
+    float4 *stage = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(sbar + 1) + 112);
     const size_t slab = (size_t)N * H;                            // float4 per z of X1 / X2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // row pencils: a quarter warp holds rows gM and gM + 4, whose storage is 64 bytes apart modulo
@@ -223,6 +231,21 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
         twM[i] = twM_g[i];
         twh_s[i] = twh_g[i];
     }
+    // one thread: both boxes of the class rows of plane (j, v) of X1 -> staging area
+    auto stage_issue = [&](int j, int v) {
+        const int jj = j / NB;
+        const int pair = jj % npairs, kx = jj / npairs;
+        const int sig = v == 0 ? 0 : (v == 1 ? 1 : nsig - 1);
+        mbar_arrive_expect_tx(sbar, (uint32_t)(2 * (rs + 1) * HC * sizeof(float4)));
+        tma_load_4d(stage, &tmapX1, sbar, 0, kx * NB + b, 0, pair * nsig + sig);
+        tma_load_4d(stage + (rs + 1) * HC, &tmapX1, sbar, 0, kx * NB + b, N - rs, pair * nsig + sig);   // last row out of bounds: zeros
+    };
+    if (STAGED && threadIdx.x == 0) {
+        mbar_init(sbar, 1);
+        mbar_fence_init();
+        if (job < njobs) stage_issue(job, 0);
+    }
+    uint32_t sphase = 0;
     uint32_t tcol = 0;
     if (STASH) {
         if (warp == 0) tmem_alloc(tslot, TCOLS);
@@ -255,6 +278,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                 const int pair = jj % npairs, kx = jj / npairs;
                 dst = X2 + (size_t)(pair * 3 + cvol) * N * slab + (size_t)kx * H;      // + z*slab + tile offset
             }
+            if (STAGED && fwd) { mbar_wait(sbar, sphase); sphase ^= 1u; }
             for (int w = warp; w < N / GM; w += NW) {
                 const int z = w * GM + gM;
                 const bool act = fwd && (z + rs) % N < nzv;
@@ -276,7 +300,13 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 #pragma unroll
                     for (int n1 = 0; n1 < EM; ++n1) {
                         const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
-                        vn[n1] = (act && ((nmask >> (2 * idx / Cfg::RN)) & 1u)) ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
+                        const bool have = act && ((nmask >> (2 * idx / Cfg::RN)) & 1u);
+                        if (STAGED) {
+                            const int zi = z <= rs ? z : z - (N - rs) + rs + 1;
+                            vn[n1] = have ? lds_c2(stage + zi * HC + idx) : c2_zero();
+                        } else {
+                            vn[n1] = have ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
+                        }
                     }
                     // a pencil group outside the support box rides along without touching shared memory
                     fft_row_adj2split<LM, EM>(vn, plane + z * P, 1, tM, tw, twh, act);
@@ -295,7 +325,13 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
         {
             int jn = job, vn = vol + 1;
             if (vn == 3 || (stash && vn == 2)) { vn = 0; jn += gridDim.x; }
-            if (jn < njobs) {
+            if (STAGED) {
+                // (a plane without phase 1 changes nothing: its successor's rows are already waiting)
+                if (threadIdx.x == 0 && jn < njobs && fwd) {
+                    fence_proxy_async_smem();
+                    stage_issue(jn, vn);
+                }
+            } else if (jn < njobs) {
                 const int jj = jn / NB;
                 const int pair = jj % npairs, kx = jj / npairs;
                 const int sig = vn == 0 ? 0 : (vn == 1 ? 1 : nsig - 1);
@@ -740,8 +776,13 @@ __global__ void cls_mask_bits_kernel(const uint8_t *__restrict__ lcc_mask, uint3
 template <int N> static constexpr size_t smem_a_cls() {
     return (size_t)2 * N * (ClsCfg<N>::RN * (N / 64) + 1) * sizeof(float2);
 }
-template <int N> static constexpr size_t smem_b_cls() {
-    return (size_t)N * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2) + 16;
+// tile + twiddle tables + the TMEM base address slot and the staging barrier (padded to 128 bytes) + `srows`
+// staging rows of 32 float4 (0 = unstaged kernel)
+template <int N> static constexpr size_t smem_b_cls(int srows = 0) {
+    return (size_t)N * 33 * sizeof(float4) + (size_t)(N + 64) * sizeof(float2) + 128 + (size_t)srows * 32 * sizeof(float4);
+}
+template <int N> static constexpr int stage_capacity_cls() {
+    return (int)((227 * 1024 / ClsCfg<N>::CTAS - 1024 - smem_b_cls<N>(0)) / (32 * sizeof(float4)));
 }
 template <int N> static constexpr size_t smem_c_cls() {
     using Cfg = ClsCfg<N>;
@@ -799,8 +840,10 @@ template <int N> static int cls_init_n(Plan *p) {
 template <int N> static int cls_init_all(Plan *p) {
     int rc = cls_init_n<N>(p);
     if (rc) return rc;
-    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_b_cls<N>()));
+    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b_cls<N>(0)));
+    PFB_CUDA(cudaFuncSetAttribute(cls_fftyz_mul_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_b_cls<N>(std::max(0, stage_capacity_cls<N>()))));
     return PFB_OK;
 }
 
@@ -826,11 +869,24 @@ template <int N> static int cls_b_n(Plan *p, int count, float2 *X2, cudaStream_t
     int grid = p->sm_count * Cfg::CTAS;
     grid -= grid % Cfg::NB;
     grid = std::min(grid, njobs);
+    static const int stage_env = getenv("PFB_B_STAGE") ? atoi(getenv("PFB_B_STAGE")) : 1;
+    const int srows = 2 * p->rs + 2;
+    const bool staged = stage_env != 0 && 2 * p->rs + 1 < N && srows <= stage_capacity_cls<N>();
+    if (staged && (p->tmapB_base != (const void *)p->A || p->tmapB_rs != p->rs || p->tmapB_nsig != p->nsig)) {
+        // X1 as [pair*nsig+sig][z][kx*NB+b][128 floats]; box = one class row x (rs + 1) consecutive z
+        int rc = make_x1_tensor_map(&p->tmapB, p->A, 128, N * Cfg::NB, N, (long)p->nsig * (p->batch / 2), p->rs + 1);
+        if (rc) return rc;
+        p->tmapB_base = p->A; p->tmapB_rs = p->rs; p->tmapB_nsig = p->nsig;
+    }
     LaunchScope ls(p, KC_FUSED_B, s);
-    cls_fftyz_mul_kernel<N><<<grid, Cfg::THREADS, smem_b_cls<N>(), s>>>(
-        reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
-        reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->cls_twN, p->cls_twM,
-        p->cls_twh, p->rs, p->nmask, p->nsig, npairs);
+    auto launch = [&](auto kernel, size_t smem) {
+        kernel<<<grid, Cfg::THREADS, smem, s>>>(
+            reinterpret_cast<const float4 *>(p->A), reinterpret_cast<float4 *>(X2),
+            reinterpret_cast<const float4 *>(p->Fq), reinterpret_cast<const float4 *>(p->F2q), p->cls_twN, p->cls_twM,
+            p->cls_twh, p->rs, p->nmask, p->nsig, npairs, p->tmapB);
+    };
+    if (staged) launch(cls_fftyz_mul_kernel<N, true>, smem_b_cls<N>(srows));
+    else launch(cls_fftyz_mul_kernel<N, false>, smem_b_cls<N>(0));
     return PFB_OK;
 }
 
