@@ -283,6 +283,17 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                 const int z = w * GM + gM;
                 const bool act = fwd && (z + rs) % N < nzv;
                 const bool any = __any_sync(0xffffffffu, act);
+                // unstaged: the next plane's row z leaves for the registers before the inverse transform of the
+                // current plane's row, which hides most of its L2 round trip (the class path has registers to spare)
+                C2 vn[EM];
+                if (!STAGED && any) {
+#pragma unroll
+                    for (int n1 = 0; n1 < EM; ++n1) {
+                        const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
+                        const bool have = act && ((nmask >> (2 * idx / Cfg::RN)) & 1u);
+                        vn[n1] = have ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
+                    }
+                }
                 if (cjob >= 0) {
                     C2 v[EM];
 #pragma unroll
@@ -296,16 +307,13 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                     }
                 }
                 if (any) {
-                    C2 vn[EM];                                                         // next plane's row z
+                    if (STAGED) {
 #pragma unroll
-                    for (int n1 = 0; n1 < EM; ++n1) {
-                        const int idx = tM + LM * n1;                                  // n = 2 idx, 2 idx + 1
-                        const bool have = act && ((nmask >> (2 * idx / Cfg::RN)) & 1u);
-                        if (STAGED) {
+                        for (int n1 = 0; n1 < EM; ++n1) {
+                            const int idx = tM + LM * n1;
+                            const bool have = act && ((nmask >> (2 * idx / Cfg::RN)) & 1u);
                             const int zi = z <= rs ? z : z - (N - rs) + rs + 1;
                             vn[n1] = have ? lds_c2(stage + zi * HC + idx) : c2_zero();
-                        } else {
-                            vn[n1] = have ? ldg_c2(src + (size_t)z * slab + idx) : c2_zero();
                         }
                     }
                     // a pencil group outside the support box rides along without touching shared memory
@@ -364,7 +372,6 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
                     if (fwd) {
                         fft_pencil2_mul_stash<false, LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN,
                                                              tcol + it * 4 * EN, stash && vol == 1);
-                        tmem_wait_st();
                     } else {
                         fft_pencil2_mul_stash<true, LN, EN>(v, plane + c, P, tN, tw, Fm + (size_t)c * N + tN,
                                                             tcol + it * 4 * EN, false);
@@ -377,6 +384,7 @@ cls_fftyz_mul_kernel(const float4 *__restrict__ X1, float4 *__restrict__ X2, con
 #pragma unroll
                 for (int m = 0; m < EN; ++m) sts_c2(plane + (tN + LN * m) * P + c, v[m]);
             }
+            if (STASH) tmem_wait_st();      // the parked spectrum is in place before this thread passes the next barrier
         }
         cjob = job; cvol = vol;
         if (++vol == 3) { vol = 0; job += gridDim.x; }
