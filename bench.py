@@ -114,7 +114,7 @@ def default_rps(w):
     if "shape" in w:
         return 4096
     # one step = one full rotational search of the named angle at 128^3 (7416 rotations); bounded blocks elsewhere
-    return {64: 2048, 128: w["full_R"], 256: 128, 192: 150}.get(n, 256)
+    return {64: 2048, 128: w["full_R"], 256: 512, 192: 808}.get(n, 256)
 
 
 def peak_hbm():

@@ -13,4 +13,6 @@ d=json.load(open('gpurun_out/bench_n$N.json'))
 print('N=%d rot/s %.0f e2e %.0f frac %.3f' % (d['n_gpus'], d['value'], d['e2e']['value'], d['roofline']['step_frac']))
 print('merge_check', d.get('merge_check'))
 print('strong', d.get('strong'))
+print('multi', d.get('multi_template'))
+print('config4_sharded', d.get('config4_sharded'))
 PY
