@@ -51,7 +51,10 @@ const char *pfb_last_error(void);
  * allocates every device buffer and FFT table for one (device, shape).
  * max_batch = rotations in flight per pass (rounded up to even; 0 = choose; halved until the work buffers fit
  * when device memory is short -- pfb_plan_info(plan, 4) reports the batch in use).
- * rmax is derived as min(nz,ny,nx)/2 (powerfitter.py:176). */
+ * rmax is derived as min(nz,ny,nx)/2 (powerfitter.py:176).
+ * Any 2.3.5.7-smooth shape up to 1024 per axis is accepted.  Shapes whose axes are 32, 64, 96 or 128 voxels long
+ * (any mix) and the cubes 192^3 and 256^3 run the fused three-kernel pipeline (pfb_plan_info(plan, 6) == 1); every
+ * other shape runs the any-shape pipeline: same results, about ten times slower. */
 int pfb_plan_create(int nz, int ny, int nx, int max_batch, int device, pfb_plan **out);
 int pfb_plan_destroy(pfb_plan *plan);
 
