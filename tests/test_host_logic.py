@@ -171,7 +171,7 @@ def test_wrapped_padding_preserves_offsets():
     assert fused_shape((100, 90, 84)) == (128, 96, 96) and fused_shape((130, 20, 20)) == (192, 192, 192)
     assert fused_shape((200, 256, 31)) == (256, 256, 256) and fused_shape((300, 10, 10)) is None
     q = pad_wrapped(a, (32, 64, 32))
-    assert q.shape == (32, 64, 32) and q.sum() == a.sum()
+    assert q.shape == (32, 64, 32) and np.array_equal(np.sort(q[q != 0]), np.sort(a.ravel()))
     for idx in [(0, 0, 0), (3, 6, 4), (9, 12, 8), (5, 7, 5), (6, 6, 4)]:
         off = [i if i <= s // 2 else i - s for i, s in zip(idx, a.shape)]
         assert q[tuple(o % n for o, n in zip(off, q.shape))] == a[idx]
