@@ -113,12 +113,23 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
     const int t = lane & (L - 1), rr = (32 / L) * warp + lane / L;
     float2 tw[E];
     load_twiddles<E>(tw, twN, t);
+    // A row outside the sphere (y = n + 64 j with j = NB / 2 always, the others away from the central z slabs)
+    // was never written by the gather: it is zero, its transforms are zero, and a warp whose rows are all of that
+    // kind skips its pencils (warp-uniform; the block barriers stay outside).
+    bool live;
+    {
+        const int iy = n0 + rr % RN + 64 * (rr / RN);
+        const int oy = iy <= N / 2 ? iy : iy - N;
+        live = __any_sync(0xffffffffu, lim2 - oy * oy - oz * oz >= 0 && oy > -(N / 2));
+    }
     float2 v[E];
+    if (live) {
 #pragma unroll
-    for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
-    fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
+        for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
+        fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
 #pragma unroll
-    for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
+        for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
+    }
     __syncthreads();
 
     // ---- fold over j and store: thread (kx, pair slot ps): rows r = 2 ps, 2 ps + 1
@@ -154,22 +165,26 @@ cls_rotate_fftx_kernel(const float4 *__restrict__ tmplq, const float *__restrict
     fold_store(tile_t, 0);
     // mask: its squares (core-weighted masks only) are parked in the template tile, which is free now
     __syncthreads();
+    if (live) {
 #pragma unroll
-    for (int n1 = 0; n1 < E; ++n1) {
-        v[n1] = tile_m[(t + L * n1) * TP + rr];
-        if (nsig == 3) tile_t[(t + L * n1) * TP + rr] = make_float2(v[n1].x * v[n1].x, v[n1].y * v[n1].y);
+        for (int n1 = 0; n1 < E; ++n1) {
+            v[n1] = tile_m[(t + L * n1) * TP + rr];
+            if (nsig == 3) tile_t[(t + L * n1) * TP + rr] = make_float2(v[n1].x * v[n1].x, v[n1].y * v[n1].y);
+        }
+        fft_pencil<E, L>(v, tile_m + rr, TP, t, tw, true);
+#pragma unroll
+        for (int m = 0; m < E; ++m) tile_m[(t + L * m) * TP + rr] = v[m];
     }
-    fft_pencil<E, L>(v, tile_m + rr, TP, t, tw, true);
-#pragma unroll
-    for (int m = 0; m < E; ++m) tile_m[(t + L * m) * TP + rr] = v[m];
     __syncthreads();
     fold_store(tile_m, 1);
     if (nsig == 3) {
+        if (live) {
 #pragma unroll
-        for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
-        fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
+            for (int n1 = 0; n1 < E; ++n1) v[n1] = tile_t[(t + L * n1) * TP + rr];
+            fft_pencil<E, L>(v, tile_t + rr, TP, t, tw, true);
 #pragma unroll
-        for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
+            for (int m = 0; m < E; ++m) tile_t[(t + L * m) * TP + rr] = v[m];
+        }
         __syncthreads();
         fold_store(tile_t, 2);
     }
