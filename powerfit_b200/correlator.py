@@ -121,9 +121,13 @@ class CUDACorrelator(object):
     """B200 implementation of the local cross-correlation search."""
 
     def __init__(self, target, device=None, laplace=False, batch=0, prep="device", pad=False, shard=False,
-                 group=None):
+                 group=None, result_rank=None):
         """``shard=True`` (opt-in): split the rotation list over the ranks of the torch.distributed process
         group ``group`` (default: the world group) and merge with one MAX all-reduce, see ``scan``.
+        ``result_rank=r`` (with ``shard=True``): only rank ``r`` of the group receives the merged grids -- a MAX
+        reduce to that rank instead of the all-reduce, and the other ranks skip the unpacking and the download
+        (their ``.lcc`` / ``.rot`` are None).  This is what the reference's multi-process search does: the worker
+        processes hand their partial grids to the parent (powerfitter.py:135-163), nobody else sees the result.
 
         ``pad=True`` (opt-in, not reference behaviour): zero-pad the map to the next grid that has a fused
         pipeline (every axis up to 32, 64, 96 or 128 voxels; 192^3 / 256^3 beyond) and crop the results back.
@@ -161,6 +165,7 @@ class CUDACorrelator(object):
         self._rot = None
         self.progress = False
         self.shard = bool(shard)    # split rotations over torch.distributed ranks (every rank must call scan())
+        self.result_rank = None if result_rank is None else int(result_rank)
         self.group = group
         self.last_scan_seconds = None
         self.last_scan_profile = None
@@ -362,7 +367,8 @@ class CUDACorrelator(object):
         torch.distributed process group each rank searches its contiguous block of the rotation list
         (powerfitter.py:95-108) and the packed best grids are merged by a single integer MAX all-reduce
         (the order-preserving key reproduces the reference's merge, powerfitter.py:146-163); every rank
-        ends with the full result.  EVERY rank of the group must call scan() with the same target,
+        ends with the full result (or, with ``result_rank`` set, only that rank: a MAX reduce, no unpacking and
+        no download elsewhere -- the reference's parent-process semantics).  EVERY rank of the group must call scan() with the same target,
         template, mask and rotations -- sharding is therefore opt-in (``shard=True`` in the constructor
         or ``PowerFitter(..., shard=True)``); without it a rank searches the whole list on its own.
         ``last_scan_profile`` holds the device-timed split of the call (search / all-reduce / unpack+download)."""
@@ -380,9 +386,24 @@ class CUDACorrelator(object):
             ev[0].record(stream)
             best = self.scan_device(lo, hi)
             ev[1].record(stream)
+            mine = True                                # does this rank receive the merged grids?
             if world > 1:
-                dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+                if self.result_rank is None:
+                    dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+                else:
+                    dst = self.result_rank if self.group is None else dist.get_global_rank(self.group, self.result_rank)
+                    dist.reduce(best, dst=dst, op=dist.ReduceOp.MAX, group=self.group)
+                    mine = rank == self.result_rank
             ev[2].record(stream)
+            if not mine:
+                ev[3].record(stream)
+                ev[3].synchronize()
+                self._lcc = self._rot = None
+                self.last_scan_seconds = time() - t0
+                self.last_scan_profile = {"rotations": int(hi - lo), "world": int(world),
+                                          "search_ms": ev[0].elapsed_time(ev[1]),
+                                          "allreduce_ms": ev[1].elapsed_time(ev[2]), "unpack_download_ms": 0.0}
+                return
             # both grids in one device buffer -> ONE DMA transfer into page-locked host memory (powerfitter.py:536-537)
             V = int(np.prod(self._shape))
             out = torch.empty(2 * V, dtype=torch.int32, device=self._device)

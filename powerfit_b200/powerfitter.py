@@ -24,10 +24,11 @@ def _array_of(obj):
 
 class PowerFitter(object):
 
-    def __init__(self, target, laplace=False, shard=False, group=None):
+    def __init__(self, target, laplace=False, shard=False, group=None, result_rank=None):
         self._target = target
         self._shard = shard
         self._group = group
+        self._result_rank = result_rank    # with shard=True: only this rank gets _lcc / _rot (see CUDACorrelator)
         self._rotations = None
         self._template = None
         self._mask = None
@@ -59,7 +60,7 @@ class PowerFitter(object):
             device = q if isinstance(q, (int, str)) or hasattr(q, "type") else None
         self._corr = CUDACorrelator(_array_of(self._target), device=device, laplace=self._laplace,
                                     batch=self._batch, pad=self.pad_to_fused, shard=self._shard,
-                                    group=self._group)
+                                    group=self._group, result_rank=self._result_rank)
         self._corr.template = _array_of(self._template)
         self._corr.mask = _array_of(self._mask)
         self._corr.rotations = self._rotations

@@ -766,6 +766,14 @@ single = CUDACorrelator(target, device=rank)         # shard=False: the whole li
 single.template, single.mask, single.rotations = template, mask, g["rotations"]
 single.scan()
 ok = ok and np.array_equal(single.lcc, c.lcc) and np.array_equal(single.rot, c.rot)
+# result_rank: a MAX reduce to one rank, the other rank gets nothing (the reference's parent-process semantics)
+root = CUDACorrelator(target, device=rank, shard=True, result_rank=1)
+root.template, root.mask, root.rotations = template, mask, g["rotations"]
+root.scan()
+if rank == 1:
+    ok = ok and np.array_equal(root.lcc, single.lcc) and np.array_equal(root.rot, single.rot)
+else:
+    ok = ok and root.lcc is None and root.rot is None
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
 """
