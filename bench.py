@@ -423,13 +423,29 @@ def sharded_config4(dev, rank, world, R=1024):
         vals = [float(v) for v in vals.tolist()]
         if best is None or vals[0] < best[0]:
             best = vals
+    nonzero, lcc_max = int(np.count_nonzero(c.lcc)), float(c.lcc.max())
+    root_best = None
+    if world > 1:                                         # the merged grids delivered to rank 0 only (see strong_search)
+        c.result_rank = 0
+        c.scan()
+        for rep in range(2):
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            c.scan()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            root_best = float(dt.item()) if root_best is None else min(root_best, float(dt.item()))
+        c.result_rank = None
     S = spectrum_bytes(w)
     peak, _ = peak_hbm()
     out = {"workload": w["desc"] + "; %d rotations sharded over %d rank(s)" % (R, world), "rotation_set": rot_desc,
            "rotations": R, "rotations_per_rank": int(c.last_scan_profile["rotations"]), "seconds": best[0],
            "rotations_per_s": R / best[0], "search_ms": best[1], "allreduce_ms": best[2], "unpack_download_ms": best[3],
            "search_frac_per_gpu": int(c.last_scan_profile["rotations"]) / (best[1] / 1e3) * 12 * S / 1e9 / peak,
-           "result": {"nonzero": int(np.count_nonzero(c.lcc)), "lcc_max": float(c.lcc.max())}}
+           "result": {"nonzero": nonzero, "lcc_max": lcc_max}}
+    if root_best is not None:
+        out.update({"seconds_result_on_rank0": root_best, "rotations_per_s_result_on_rank0": R / root_best})
     del c
     torch.cuda.empty_cache()
     return out
