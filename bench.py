@@ -481,6 +481,20 @@ def multi_template_search(dev, rank, world, rot_per_template=2000):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         best = float(dt.item()) if best is None else min(best, float(dt.item()))
+    lcc_max = [float(x.max()) for x in m.lccs]
+    root_best = None
+    if world > 1:                                        # all four result grids delivered to rank 0 only
+        m.result_rank = 0
+        m.scan_all()
+        for rep in range(2):
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            m.scan_all()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            root_best = float(dt.item()) if root_best is None else min(root_best, float(dt.item()))
+        m.result_rank = None
     total = len(subunits) * rot_per_template
     S = 8 * n * n * (n // 2 + 1)
     peak, _ = peak_hbm()
@@ -489,7 +503,10 @@ def multi_template_search(dev, rank, world, rot_per_template=2000):
            "templates": len(subunits), "rotations_total": total, "rotations_this_rank": int(m.last_scan_rotations),
            "seconds": best, "rotations_per_s": total / best,
            "step_frac_per_gpu": total / best / world * 10 * S / 1e9 / peak,
-           "lcc_max_per_template": [float(x.max()) for x in m.lccs]}
+           "lcc_max_per_template": lcc_max}
+    if root_best is not None:
+        out.update({"seconds_result_on_rank0": root_best, "rotations_per_s_result_on_rank0": total / root_best,
+                    "step_frac_per_gpu_result_on_rank0": total / root_best / world * 10 * S / 1e9 / peak})
     del m
     torch.cuda.empty_cache()
     return out

@@ -519,7 +519,8 @@ class MultiTemplateCorrelator(CUDACorrelator):
 
     ``scan_all()`` searches every template over ``.rotations``.  With ``shard=True`` under torch.distributed the
     (template, rotation block) work items are dealt over the ranks and ALL templates' packed best grids are
-    merged by one MAX all-reduce of the [T, V] int64 tensor."""
+    merged by one MAX all-reduce of the [T, V] int64 tensor (``result_rank=r``: a MAX reduce to rank r, which alone
+    unpacks and downloads the grids)."""
 
     _SLOT_ATTRS = ("_template_h", "_template_set", "_mask", "_mask_binary", "_norm_factor", "_d_template", "_d_mask")
 
@@ -579,7 +580,18 @@ class MultiTemplateCorrelator(CUDACorrelator):
                                                best[t].data_ptr(), self._stream()))
                 done += hi - lo
             if world > 1:
-                dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+                if self.result_rank is None:
+                    dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+                else:                                  # results on one rank only (see CUDACorrelator)
+                    dst = self.result_rank if self.group is None else dist.get_global_rank(self.group, self.result_rank)
+                    dist.reduce(best, dst=dst, op=dist.ReduceOp.MAX, group=self.group)
+                    if rank != self.result_rank:
+                        torch.cuda.current_stream(self._device).synchronize()
+                        self.lccs, self.rots = [None] * T, [None] * T
+                        self._lcc = self._rot = None
+                        self.last_scan_seconds = time() - t0
+                        self.last_scan_rotations = done
+                        return
             # all grids in one device buffer -> one DMA transfer into page-locked host memory
             out = torch.empty(2 * T * V, dtype=torch.int32, device=self._device)
             d_lcc, d_rot = out[:T * V].view(torch.float32).view(T, V), out[T * V:].view(T, V)
