@@ -100,11 +100,16 @@ R = g["rotations"]
 lo, hi = shard_bounds(len(R), 2, dist.get_rank())
 c = O.OracleCorrelator(target); c.template = template; c.mask = mask; c.rotations = R[lo:hi]; c.scan()
 key = torch.from_numpy(P.pack(c.lcc.astype(np.float32), c.rot + lo))
+root_key = key.clone()
 dist.all_reduce(key, op=dist.ReduceOp.MAX)
 lcc, rot = P.unpack(key.numpy())
 ok = np.allclose(lcc, g["lcc"], atol=1e-6)
 decided = (g["lcc"] - g["lcc2"]) > 1e-6
 ok = ok and np.array_equal(rot[decided], g["rot"][decided])
+# result_rank: a MAX reduce to one rank gives that rank the same merged grid (CUDACorrelator(result_rank=1))
+dist.reduce(root_key, dst=1, op=dist.ReduceOp.MAX)
+if dist.get_rank() == 1:
+    ok = ok and np.array_equal(root_key.numpy(), key.numpy())
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
 """
